@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- LU GFLOP/s (2n^3/3) for NxN Float64 on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 16384]
+
+One "step" = one LU factorization with partial pivoting of a fresh copy of the same synthetic
+U[0,1) matrix (numpy default_rng(12), the distribution of test/runtests.jl:45).
+
+ours:       value = device-resident throughput (matrix already in HBM, CUDA events on the library's
+            stream around each factorization; the restore copy between steps is outside the timed
+            region); e2e = the same metric through the public host API (`rfb200.lu_` on a pinned host
+            matrix: H2D + LU + D2H inside the timed region).
+reference:  the reference is pure Julia and cannot run here (no Julia runtime), so
+            this arm times the CPU oracle port of its algorithm (oracle/rf_oracle.c, all host cores)
+            on a bounded sample of the same workload.
+
+N > 1 (torchrun, one process per GPU): until the 1-D block-cyclic driver lands each rank factors its
+own replica (weak scaling, no data-path collective); value = total flops / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LU GFLOP/s (2n^3/3) for NxN Float64; residual ||PA-LU||_F/||A||_F"
+
+
+def lu_flops(n):
+    return 2.0 * n ** 3 / 3.0
+
+
+def fill_random(a, seed=12, chunk=1024):
+    """U[0,1) entries, generated per column block so the 2 GB matrix never exists twice."""
+    n = a.shape[1]
+    for j0 in range(0, n, chunk):
+        j1 = min(n, j0 + chunk)
+        rng = np.random.default_rng([seed, j0 // chunk])
+        a[:, j0:j1] = rng.random((a.shape[0], j1 - j0), dtype=a.dtype).reshape(a.shape[0], j1 - j0)
+
+
+def hutchinson_residual(a0, factors, ipiv, nvec=8, seed=0):
+    """Estimate ||P A - L U||_F / ||A||_F with random +-1 probes (O(n^2) per probe, no oracle needed)."""
+    rng = np.random.default_rng(seed)
+    m, n = a0.shape
+    p = np.arange(m)
+    for i, ip in enumerate(ipiv):
+        ip = int(ip) - 1
+        if ip != i:
+            p[i], p[ip] = p[ip], p[i]
+    mn = min(m, n)
+    x = rng.integers(0, 2, size=(n, nvec)).astype(np.float64) * 2 - 1
+    ux = np.triu(factors[:mn, :]) @ x
+    lux = np.tril(factors[:, :mn], -1) @ ux
+    lux[:mn] += ux
+    pax = a0[p, :] @ x
+    return float(np.linalg.norm(pax - lux) / np.sqrt(nvec) / np.linalg.norm(a0))
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(smax), power_w_max=max(power),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline(n_sample, threads, reps=1):
+    """Oracle port (restatement of the reference algorithm, reference defaults) on the host cores."""
+    from oracle import rf_oracle as O
+    a0 = np.empty((n_sample, n_sample), dtype=np.float64, order="F")
+    fill_random(a0)
+    best = None
+    for _ in range(reps):
+        a = a0.copy(order="F")
+        t = time.perf_counter()
+        O.lu_c(a, threads=threads)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return lu_flops(n_sample) / best / 1e9, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import rf_oracle as O
+    cores = os.cpu_count() or 1
+    # calibrate on a small case, then size the sample so the whole run stays within ~2.5 minutes
+    gf_small, _ = cpu_baseline(2048, cores)
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    n_s = 2048
+    for cand in (3072, 4096, 6144, 8192, 12288, 16384):
+        if cand <= args.n and lu_flops(cand) / (gf_small * 1e9) <= budget_s:
+            n_s = cand
+    a0 = np.empty((n_s, n_s), dtype=np.float64, order="F")
+    fill_random(a0)
+    times = []
+    for it in range(args.warmup + args.steps):
+        a = a0.copy(order="F")
+        t = time.perf_counter()
+        O.lu_c(a, threads=cores)
+        dt = time.perf_counter() - t
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = lu_flops(n_s) / (ms * 1e-3) / 1e9
+    sample = (f"{n_s}x{n_s} Float64 U[0,1) LU per step (bounded sample of the {args.n}x{args.n} workload), "
+              f"oracle/rf_oracle.c = C restatement of src/lu.jl with reference defaults (blocksize 8, threshold 48), "
+              f"OpenMP {cores} threads; the Julia reference itself cannot run here")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.n}x{args.n} Float64 LU with partial pivoting", "sample_n": n_s},
+        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import rfb200
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.n
+    ctx = rfb200.Context(local_rank)
+    dev = ctx.device_info()
+    host = ctx.pinned_empty((n, n), np.float64)
+    fill_random(host)
+    pristine = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
+    work = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
+    pristine.upload(host)
+    ctx.sync()
+
+    dmma_peak = ctx.dmma_peak_tflops(20000)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        work.copy_from(pristine)
+        work.lu()
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    times = []
+    for _ in range(args.steps):
+        work.copy_from(pristine)           # restore (LU is in place); outside the timed region
+        ctx.timer_start()
+        work.lu()
+        times.append(ctx.timer_stop())
+    ctx.sync()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    ms = max_over_ranks(sum(times) / len(times))
+    value = world * lu_flops(n) / (ms * 1e-3) / 1e9
+
+    # ---- correctness of what was just timed ---------------------------------------------------
+    f, ipiv, info = work.download()
+    res = hutchinson_residual(host, f, ipiv)
+    lmax = float(np.abs(np.tril(f, -1)).max())
+    checks = {"info": info, "residual_fro_rel_est": res, "bound_20_n_eps": 20 * n * float(np.finfo(np.float64).eps),
+              "max_abs_L": lmax}
+    if args.check_pivots:
+        from scipy.linalg import lapack
+        _, piv, _ = lapack.dgetrf(np.array(host, order="F", copy=True), overwrite_a=True)
+        checks["pivots_equal_lapack"] = bool(np.array_equal(ipiv, piv + 1))
+    del f
+
+    # ---- per-kernel-class profile (events around every launch; separate, untimed pass) ---------
+    work.copy_from(pristine)
+    ctx.profile_enable(True)
+    work.lu()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    gemm = prof["gemm"]
+    gemm_tf = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "K4 trailing GEMM (FP64 DMMA mma.sync m8n8k4; tcgen05 has no f64 kind)",
+        "achieved": gemm_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": gemm_tf / dmma_peak if dmma_peak else None,
+        "traffic": traffic,
+        "peak_source": "own register-only DMMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
+                       "nominal B200 FP64 37 TFLOP/s",
+        "achieved_def": "sum of 2mnk over all GEMM launches of one LU / sum of their CUDA-event durations",
+        "share_of_step_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "launches_by_class": {k: v["launches"] for k, v in prof.items()},
+    }
+
+    # ---- end to end through the public host API (pinned host buffers) --------------------------
+    e2e = None
+    if not args.skip_e2e:
+        hwork = ctx.pinned_empty((n, n), np.float64)
+        ipiv_h = np.empty(n, dtype=np.int64)
+        et = []
+        for it in range(1 + min(args.steps, 3)):
+            np.copyto(hwork, host)
+            barrier()
+            t = time.perf_counter()
+            rfb200.lu_(hwork, ipiv_h, ctx=ctx)
+            dt = time.perf_counter() - t
+            if it > 0:
+                et.append(dt)
+        e_ms = max_over_ranks(1e3 * sum(et) / len(et))
+        e2e = {"value": world * lu_flops(n) / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + n * 8 + 8}
+
+    # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
+    cpu = None
+    if rank == 0 and not args.skip_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_s = min(n, args.cpu_sample_n)
+        gf, secs = cpu_baseline(n_s, cores)
+        cpu = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "seconds": secs,
+               "sample": f"{n_s}x{n_s} Float64 U[0,1) LU, oracle/rf_oracle.c (C restatement of src/lu.jl, reference "
+                         f"defaults), OpenMP {cores} threads; the Julia reference cannot run here"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n}x{n} Float64 LU with partial pivoting, 1 matrix per GPU",
+                       "input": "U[0,1) numpy default_rng([12, block]) column-major, lda = n",
+                       "parallelism": "replicas" if world > 1 else "1 GPU",
+                       "l2": f"input {n * n * 8 / 1e6:.0f} MB > 126 MB L2; matrix restored by an untimed d2d copy between steps",
+                       "device": dev},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "checks": checks, "dmma_peak_tflops": dmma_peak,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--cpu-sample-n", type=int, default=8192)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--check-pivots", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+/*
+ * rfb200.h -- C ABI of librfb200.so: B200-native (sm_100a) recursive left-looking LU with partial
+ * pivoting, the drop-in for the hot path of RecursiveFactorization.jl (`lu` / `lu!`).
+ *
+ * Reference citations are relative to /root/reference (RecursiveFactorization.jl 0.2.30).
+ *
+ * Conventions
+ *   - every function returns an int status (RFB_OK == 0); numerical singularity is NOT an error:
+ *     it is reported through `info` exactly like src/lu.jl:321-327 / :248-255 (0 = ok, k > 0 = first
+ *     exactly-zero pivot at global column k, factorization continues).  Throwing
+ *     SingularException (src/lu.jl:128 `checknonsingular`) is the caller's (Julia / Python) job.
+ *   - matrices are column-major with leading dimension `lda` (elements); `ipiv` is int64
+ *     (= Julia BlasInt), 1-based, sequential-swap (LAPACK) semantics, length min(m, n):
+ *     byte-for-byte what `LinearAlgebra.LU.ipiv` holds (src/lu.jl:129).
+ *   - the library never keeps a host pointer past the call and never frees caller memory.
+ *   - there is no CPU fallback: without a usable sm_100 device rfb_create fails.
+ *   - a context is not thread-safe; use one per host thread / Julia task.
+ */
+#ifndef RFB200_H
+#define RFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rfb_ctx rfb_ctx;
+
+enum {
+    RFB_OK = 0,
+    RFB_ERR_ARG = 1,         /* bad argument (null pointer, lda < m, ...)                     */
+    RFB_ERR_CUDA = 2,        /* CUDA runtime / driver failure; see rfb_last_error             */
+    RFB_ERR_NCCL = 3,        /* NCCL failure (multi-GPU path)                                 */
+    RFB_ERR_UNSUPPORTED = 4, /* shape / option outside what the kernels implement             */
+    RFB_ERR_NOMEM = 5,       /* device allocation failed                                      */
+    RFB_ERR_INTERNAL = 6     /* device-side protocol error (e.g. panel exchange timed out)    */
+};
+
+enum { RFB_MEM_HOST = 0, RFB_MEM_DEVICE = 1 };
+
+/* Float32 trailing-update arithmetic (config "8192x8192 Float32"). */
+enum {
+    RFB_F32_FP32 = 0,   /* exact FP32 FFMA tiles (default until the tcgen05 path lands)       */
+    RFB_F32_TF32X3 = 1  /* tcgen05 kind::tf32, 3-term split, FP32 accumulate in TMEM          */
+};
+
+/* Options of the whole-path calls.  Zero-initialise for defaults.
+ * The reference's `blocksize` / `threshold` keywords (src/lu.jl:101-102) tune a CPU register
+ * kernel; here the analogous knob is `leaf_width` (columns factored by one panel-kernel launch). */
+typedef struct rfb_opts {
+    int32_t mem_space;   /* RFB_MEM_HOST: A/ipiv are host pointers (copied in and out);
+                            RFB_MEM_DEVICE: A/ipiv are device pointers, nothing is copied     */
+    int32_t leaf_width;  /* 0 = default (64); one of 16, 32, 64                               */
+    int32_t f32_mode;    /* RFB_F32_*                                                         */
+    int32_t trsm_block;  /* 0 = default; diagonal block of the blocked TRSM                   */
+    int32_t gemm_path;   /* 0 = auto, 1 = force generic (cp.async) tiles, 2 = force TMA tiles */
+    int32_t laswp_path;  /* 0 = auto, 1 = force the ipiv-driven kernel                        */
+    int32_t reserved[10];
+} rfb_opts;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int rfb_version(void);
+int rfb_create(rfb_ctx **out, int device);            /* one stream + workspace on `device`   */
+int rfb_destroy(rfb_ctx *ctx);
+const char *rfb_last_error(rfb_ctx *ctx);             /* valid until the next call on ctx     */
+int rfb_device_info(rfb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *mem_bytes);
+
+/* ---- whole path: twin of lu!(A, ipiv, Val(true), thread; check=false)  src/lu.jl:97-156 ----
+ * Factors the m x n matrix in place (L strictly below the diagonal, U on/above: the layout of
+ * `LU.factors`), writes min(m,n) pivots and *info.  With RFB_MEM_HOST the matrix is copied to
+ * the device, factored there and copied back; with RFB_MEM_DEVICE it is factored where it lies
+ * and the call returns after enqueueing (use rfb_sync). */
+int rfb_lu_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+               int64_t *info, const rfb_opts *opts);
+int rfb_lu_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+               int64_t *info, const rfb_opts *opts);
+
+/* ---- kernel level: what a host-side restatement of reckernel! (src/lu.jl:189-263) calls. ----
+ * All pointers are DEVICE pointers into one column-major allocation sharing `lda`; calls are
+ * enqueued on the context stream and do not synchronise.
+ *
+ * rfb_panel_getrf: src/lu.jl:290-338 (_generic_lufact!) on an m x n panel, n <= 64, m >= n.
+ *   ipiv_dev[k] = (block-local 1-based pivot row) + ipiv_add;  if the k-th pivot is exactly zero
+ *   and *info_dev == 0 then *info_dev = col_offset + k + 1.
+ * rfb_laswp: src/lu.jl:164-188 (apply_permutation!): for i in 0..npiv-1 swap rows i and
+ *   ipiv_dev[i] - 1 - ipiv_sub of the (rows x ncols) block at A.
+ * rfb_trsm_llnu: TriangularSolve.ldiv!(UnitLowerTriangular(L), B) (call sites src/lu.jl:235,:153):
+ *   B (k x nrhs) <- L^-1 B, reading only the strict lower triangle of the k x k block at L.
+ * rfb_gemm_nn_sub: src/lu.jl:265-284 (schur_complement!): C (m x n) <- C - A (m x k) * B (k x n),
+ *   product accumulated from zero and added to C once.
+ * rfb_ipiv_shift: src/lu.jl:256-260 (P2 .+= n1).
+ */
+int rfb_panel_getrf_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda,
+                        int64_t *ipiv_dev, int64_t ipiv_add, int64_t *info_dev, int64_t col_offset);
+int rfb_panel_getrf_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda,
+                        int64_t *ipiv_dev, int64_t ipiv_add, int64_t *info_dev, int64_t col_offset);
+int rfb_laswp_f64(rfb_ctx *ctx, double *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
+                  int64_t npiv, int64_t ipiv_sub);
+int rfb_laswp_f32(rfb_ctx *ctx, float *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
+                  int64_t npiv, int64_t ipiv_sub);
+int rfb_trsm_llnu_f64(rfb_ctx *ctx, const double *L, int64_t k, double *B, int64_t nrhs, int64_t lda);
+int rfb_trsm_llnu_f32(rfb_ctx *ctx, const float *L, int64_t k, float *B, int64_t nrhs, int64_t lda);
+int rfb_gemm_nn_sub_f64(rfb_ctx *ctx, double *C, const double *A, const double *B, int64_t m,
+                        int64_t n, int64_t k, int64_t lda);
+int rfb_gemm_nn_sub_f32(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m,
+                        int64_t n, int64_t k, int64_t lda);
+int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);
+
+/* ---- memory / stream plumbing ------------------------------------------------------------- */
+int rfb_malloc(rfb_ctx *ctx, void **dev_ptr, size_t bytes);
+int rfb_free(rfb_ctx *ctx, void *dev_ptr);
+int rfb_host_alloc(rfb_ctx *ctx, void **host_ptr, size_t bytes);   /* pinned host memory       */
+int rfb_host_free(rfb_ctx *ctx, void *host_ptr);
+int rfb_h2d(rfb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* async        */
+int rfb_d2h(rfb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);   /* async        */
+int rfb_d2d(rfb_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);    /* async        */
+int rfb_memset(rfb_ctx *ctx, void *dst_dev, int value, size_t bytes);           /* async        */
+int rfb_sync(rfb_ctx *ctx);
+
+/* ---- measurement helpers (CUDA events on the context stream) ------------------------------- */
+int rfb_timer_start(rfb_ctx *ctx);
+int rfb_timer_stop(rfb_ctx *ctx, float *ms);              /* synchronises                      */
+int rfb_launch_count(rfb_ctx *ctx, int64_t *count);       /* kernels launched so far by ctx    */
+/* accumulated device time per kernel class since the last reset, when profiling is enabled
+ * (classes: 0 panel, 1 laswp, 2 trsm-diagonal, 3 gemm, 4 other) */
+int rfb_profile_enable(rfb_ctx *ctx, int on);
+int rfb_profile_read(rfb_ctx *ctx, double ms_by_class[8], int64_t launches_by_class[8],
+                     double work_by_class[8]);  /* algorithmic flops (bytes for laswp) issued */
+/* register-only DMMA (mma.sync m8n8k4 f64) throughput: the FP64 roofline denominator */
+int rfb_bench_dmma_peak(rfb_ctx *ctx, int iters, double *tflops);
+/* plain device copy bandwidth (read + write bytes / time) */
+int rfb_bench_copy(rfb_ctx *ctx, size_t bytes, int iters, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFB200_H */

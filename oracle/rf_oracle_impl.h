@@ -1,0 +1,230 @@
+/*
+ * rf_oracle_impl.h -- type-generic body of the CPU oracle (TEST INFRASTRUCTURE, not product).
+ *
+ * Included twice by rf_oracle.c with
+ *     #define RFO_T      double | float
+ *     #define RFO_(name) name##_f64 | name##_f32
+ *
+ * Every function cites the reference lines it restates (paths relative to
+ * /root/reference).  Parity status: see the header of rf_oracle.c.
+ */
+
+/* ---- src/lu.jl:290-338  _generic_lufact!(A, Val(true), ipiv, info) -------------------------
+ * Unblocked right-looking LU of the m x n block A with npiv = length(ipiv) pivot steps.
+ * pivot = FIRST index of the strict maximum |A[i,k]| starting from amax = 0 (:296-305);
+ * swap rows k,kp over all n columns of the block (:308-315); scale by the RECIPROCAL
+ * (:317-320); info = first k with an exactly-zero pivot, factorization continues (:321-327);
+ * rank-1 update of the remaining columns (:330-334).  ipiv is 1-based and block-local. */
+static int64_t RFO_(rfo_generic_lufact)(RFO_T *A, int64_t m, int64_t n, int64_t lda,
+                                        int64_t *ipiv, int64_t npiv, int64_t info)
+{
+    for (int64_t k = 0; k < npiv; ++k) {
+        RFO_T *ck = A + k * lda;
+        int64_t kp = k;
+        RFO_T amax = (RFO_T)0;
+        for (int64_t i = k; i < m; ++i) {
+            RFO_T absi = ck[i] < 0 ? -ck[i] : ck[i];
+            if (absi > amax) { kp = i; amax = absi; }   /* NaN never wins: (NaN > x) is false */
+        }
+        ipiv[k] = kp + 1;
+        if (ck[kp] != (RFO_T)0) {                        /* !iszero: NaN counts as non-zero */
+            if (k != kp) {
+                for (int64_t j = 0; j < n; ++j) {
+                    RFO_T t = A[k + j * lda];
+                    A[k + j * lda] = A[kp + j * lda];
+                    A[kp + j * lda] = t;
+                }
+            }
+            RFO_T inv = (RFO_T)1 / ck[k];
+            for (int64_t i = k + 1; i < m; ++i) ck[i] *= inv;
+        } else if (info == 0) {
+            info = k + 1;
+        }
+        if (k == npiv - 1) break;
+        for (int64_t j = k + 1; j < n; ++j) {
+            RFO_T *cj = A + j * lda;
+            RFO_T akj = cj[k];
+            #pragma omp simd
+            for (int64_t i = k + 1; i < m; ++i) cj[i] -= ck[i] * akj;
+        }
+    }
+    return info;
+}
+
+/* ---- src/lu.jl:164-188  apply_permutation!(P, A, thread) ------------------------------------
+ * Sequential row interchanges i <-> P[i] (1-based, local to A's first row) on an m x ncols
+ * block.  The threaded form (:164-175) walks columns in parallel, the serial form (:177-188)
+ * walks swaps and skips i' == i; both give the same result. */
+static void RFO_(rfo_apply_permutation)(const int64_t *P, int64_t np, RFO_T *A, int64_t ncols,
+                                        int64_t lda, int threads)
+{
+    #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
+    for (int64_t j = 0; j < ncols; ++j) {
+        RFO_T *c = A + j * lda;
+        for (int64_t i = 0; i < np; ++i) {
+            int64_t ip = P[i] - 1;
+            RFO_T t = c[i]; c[i] = c[ip]; c[ip] = t;
+        }
+    }
+}
+
+/* ---- src/lu.jl:265-284  schur_complement!(C, A, B, thread) ----------------------------------
+ * C[m,n] = C[m,n] + (0 - sum_k A[m,k] B[k,n]): the product is accumulated in its own register
+ * and added to C once (:269-273).  Register tiling only, no packing, like the @turbo loop nest;
+ * column blocks are spread over threads like @tturbo. */
+#define RFO_MR 16
+#define RFO_NR 4
+RFO_CLONES
+static void RFO_(rfo_schur_tile)(RFO_T *C, const RFO_T *A, const RFO_T *B, int64_t m, int64_t nn,
+                                 int64_t k, int64_t lda)
+{
+    /* nn <= RFO_NR columns of C */
+    int64_t i0 = 0;
+    for (; i0 + RFO_MR <= m; i0 += RFO_MR) {
+        RFO_T acc[RFO_NR][RFO_MR];
+        for (int c = 0; c < RFO_NR; ++c)
+            for (int r = 0; r < RFO_MR; ++r) acc[c][r] = (RFO_T)0;
+        if (nn == RFO_NR) {
+            for (int64_t kk = 0; kk < k; ++kk) {
+                const RFO_T *a = A + i0 + kk * lda;
+                for (int c = 0; c < RFO_NR; ++c) {
+                    RFO_T b = B[kk + c * lda];
+                    #pragma omp simd
+                    for (int r = 0; r < RFO_MR; ++r) acc[c][r] -= a[r] * b;
+                }
+            }
+        } else {
+            for (int64_t kk = 0; kk < k; ++kk) {
+                const RFO_T *a = A + i0 + kk * lda;
+                for (int c = 0; c < nn; ++c) {
+                    RFO_T b = B[kk + c * lda];
+                    #pragma omp simd
+                    for (int r = 0; r < RFO_MR; ++r) acc[c][r] -= a[r] * b;
+                }
+            }
+        }
+        for (int c = 0; c < nn; ++c)
+            for (int r = 0; r < RFO_MR; ++r) C[i0 + r + c * lda] = acc[c][r] + C[i0 + r + c * lda];
+    }
+    for (; i0 < m; ++i0) {
+        for (int c = 0; c < nn; ++c) {
+            RFO_T acc = (RFO_T)0;
+            for (int64_t kk = 0; kk < k; ++kk) acc -= A[i0 + kk * lda] * B[kk + c * lda];
+            C[i0 + c * lda] = acc + C[i0 + c * lda];
+        }
+    }
+}
+
+static void RFO_(rfo_schur_complement)(RFO_T *C, const RFO_T *A, const RFO_T *B, int64_t m,
+                                       int64_t n, int64_t k, int64_t lda, int threads)
+{
+    int64_t nblk = (n + RFO_NR - 1) / RFO_NR;
+    #pragma omp parallel for schedule(dynamic, 4) num_threads(threads) if (threads > 1)
+    for (int64_t jb = 0; jb < nblk; ++jb) {
+        int64_t j0 = jb * RFO_NR;
+        int64_t nn = n - j0 < RFO_NR ? n - j0 : RFO_NR;
+        RFO_(rfo_schur_tile)(C + j0 * lda, A, B + j0 * lda, m, nn, k, lda);
+    }
+}
+
+/* ---- TriangularSolve.ldiv!(UnitLowerTriangular(A11), A12, thread) ---------------------------
+ * Call sites src/lu.jl:235 and :153.  TriangularSolve.jl is an un-vendored dependency
+ * (Project.toml:23, compat 0.2.5, no Manifest => exact version unpinned).  Its published
+ * algorithm for the left/unit-lower case is block forward substitution: solve a diagonal block
+ * by substitution, then subtract its contribution from the rows below.  Restated here with
+ * block size RFO_TB and the accumulate-then-add update above.  Only the STRICT lower triangle
+ * of L is read (its diagonal and upper part hold U). */
+#define RFO_TB 64
+static void RFO_(rfo_trsm_llnu)(const RFO_T *L, int64_t k, RFO_T *B, int64_t nrhs, int64_t lda,
+                                int threads)
+{
+    for (int64_t b0 = 0; b0 < k; b0 += RFO_TB) {
+        int64_t bs = k - b0 < RFO_TB ? k - b0 : RFO_TB;
+        #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
+        for (int64_t j = 0; j < nrhs; ++j) {
+            RFO_T *x = B + b0 + j * lda;
+            for (int64_t c = 0; c < bs; ++c) {
+                const RFO_T *l = L + b0 + (b0 + c) * lda;
+                RFO_T xc = x[c];
+                #pragma omp simd
+                for (int64_t r = c + 1; r < bs; ++r) x[r] -= l[r] * xc;
+            }
+        }
+        int64_t rest = k - b0 - bs;
+        if (rest > 0)
+            RFO_(rfo_schur_complement)(B + b0 + bs, L + b0 + bs + b0 * lda, B + b0, rest, nrhs, bs,
+                                       lda, threads);
+    }
+}
+
+/* ---- src/lu.jl:158-162  nsplit(T, n) --------------------------------------------------------*/
+static int64_t RFO_(rfo_nsplit)(int64_t n)
+{
+    int64_t k = 128 / (int64_t)sizeof(RFO_T);
+    if (k < 2) k = 2;
+    int64_t k2 = k / 2;
+    return n >= k ? ((n + k2) / k) * k2 : n / 2;
+}
+
+/* ---- src/lu.jl:189-263  reckernel!(A, Val(true), m, n, ipiv, info, blocksize, thread) -------*/
+static int64_t RFO_(rfo_reckernel)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+                                   int64_t info, int64_t blocksize, int threads)
+{
+    if (n <= (blocksize > 1 ? blocksize : 1))                                   /* :192-195 */
+        return RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, n, info);
+    int64_t n1 = RFO_(rfo_nsplit)(n), n2 = n - n1, m2 = m - n1;                 /* :196-198 */
+    RFO_T *AR = A + n1 * lda, *A21 = A + n1, *A22 = A + n1 + n1 * lda;          /* :210-218 */
+    int64_t *P1 = ipiv, *P2 = ipiv + n1;                                        /* :221-222 */
+    info = RFO_(rfo_reckernel)(A, m, n1, lda, P1, info, blocksize, threads);    /* :229 */
+    RFO_(rfo_apply_permutation)(P1, n1, AR, n2, lda, threads);                  /* :233 */
+    RFO_(rfo_trsm_llnu)(A, n1, AR, n2, lda, threads);                           /* :235 */
+    RFO_(rfo_schur_complement)(A22, A21, AR, m2, n2, n1, lda, threads);         /* :240 */
+    int64_t previnfo = info;                                                    /* :242 */
+    info = RFO_(rfo_reckernel)(A22, m2, n2, lda, P2, info, blocksize, threads); /* :244 */
+    RFO_(rfo_apply_permutation)(P2, n2, A21, n1, lda, threads);                 /* :246 */
+    if (info != previnfo) info += n1;                                           /* :248-255 */
+    for (int64_t i = 0; i < n2; ++i) P2[i] += n1;                               /* :256-260 */
+    return info;
+}
+
+/* ---- src/lu.jl:97-130 (driver) + :145-156 (_recurse!, fat tail) -----------------------------
+ * blocksize <= 0 selects the reference default (length(A) >= 40000 ? 8 : 16, :101);
+ * threshold <= 0 selects pick_threshold() for a 64-byte SIMD register, i.e. 48 (:90,:102).
+ * Returns info; never throws (checknonsingular, :128, is the caller's job). */
+int64_t RFO_(rfo_lu)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+                     int64_t blocksize, int64_t threshold, int threads)
+{
+    if (blocksize <= 0) blocksize = (m * n >= 40000) ? 8 : 16;
+    if (threshold <= 0) threshold = 48;
+    if (threads < 1) threads = 1;
+    int64_t mn = m < n ? m : n, info = 0;
+    if (mn == 0) return 0;
+    if (mn > threshold) {                                                       /* :114 */
+        info = RFO_(rfo_reckernel)(A, m, mn, lda, ipiv, info, blocksize, threads); /* :147 */
+        if (m < n) {                                                            /* :148-154 */
+            RFO_T *AR = A + m * lda;
+            RFO_(rfo_apply_permutation)(ipiv, mn, AR, n - m, lda, threads);
+            RFO_(rfo_trsm_llnu)(A, m, AR, n - m, lda, threads);
+        }
+    } else {
+        info = RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, mn, info);          /* :125-126 */
+    }
+    return info;
+}
+
+/* Kernel-level entry points so the tests can check each CUDA kernel against the matching
+ * restated loop in isolation. */
+int64_t RFO_(rfo_panel)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t info)
+{ return RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, n < m ? n : m, info); }
+void RFO_(rfo_laswp)(RFO_T *A, int64_t ncols, int64_t lda, const int64_t *ipiv, int64_t np)
+{ RFO_(rfo_apply_permutation)(ipiv, np, A, ncols, lda, 1); }
+void RFO_(rfo_trsm)(const RFO_T *L, int64_t k, RFO_T *B, int64_t nrhs, int64_t lda, int threads)
+{ RFO_(rfo_trsm_llnu)(L, k, B, nrhs, lda, threads < 1 ? 1 : threads); }
+void RFO_(rfo_schur)(RFO_T *C, const RFO_T *A, const RFO_T *B, int64_t m, int64_t n, int64_t k,
+                     int64_t lda, int threads)
+{ RFO_(rfo_schur_complement)(C, A, B, m, n, k, lda, threads < 1 ? 1 : threads); }
+int64_t RFO_(rfo_nsplit_pub)(int64_t n) { return RFO_(rfo_nsplit)(n); }
+
+#undef RFO_MR
+#undef RFO_NR
+#undef RFO_TB

@@ -1,0 +1,382 @@
+"""rfb200 -- B200-native recursive LU, host-side mirror of RecursiveFactorization.jl's `lu` / `lu!`.
+
+The product is ``librfb200.so`` (hand-written sm_100a kernels behind the C ABI in
+``include/rfb200.h``).  This package is the thin host layer a Python caller uses, shaped like the
+reference's Julia API (paths relative to /root/reference):
+
+===========================  =====================================================================
+``lu(A, pivot, thread, ...)``   src/lu.jl:19-21   -- factor a copy
+``lu_(A, ipiv, pivot, ...)``    src/lu.jl:67-83 and :97-130 (``lu!``) -- factor in place
+``LU``                          LinearAlgebra.LU built at src/lu.jl:129 (factors / ipiv / info, L U p)
+``SingularException``           raised by ``checknonsingular(info)`` at src/lu.jl:128 when ``check``
+===========================  =====================================================================
+
+Arrays follow Julia's layout: column-major (Fortran-ordered) ``float64`` / ``float32``.  Pivots are
+int64, 1-based, sequential-swap -- ``LinearAlgebra.LU.ipiv``.  There is no CPU fallback anywhere:
+without the CUDA library or without a B200 every call raises.
+
+Import name: the directory is called ``recursivefactorization.jl_b200`` (not importable as is because
+of the dot); ``import rfb200`` (repo-root shim) loads it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import rfb_opts  # noqa: F401  (re-export)
+
+__all__ = [
+    "lu", "lu_", "LU", "SingularException", "RfbError", "Context", "default_context", "DeviceMatrix",
+    "nsplit", "RowMaximum", "NoPivot",
+]
+
+
+# ----------------------------------------------------------------------------------------------
+# errors
+# ----------------------------------------------------------------------------------------------
+class RfbError(RuntimeError):
+    """Non-numerical failure reported by librfb200 (bad argument, CUDA error, unsupported shape)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{_lib.STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class SingularException(ArithmeticError):
+    """LinearAlgebra.SingularException(info): U[info, info] is exactly zero (src/lu.jl:128)."""
+
+    def __init__(self, info: int):
+        super().__init__(f"matrix is singular to working precision: zero pivot at column {info}")
+        self.info = info
+
+
+class RowMaximum:   # LinearAlgebra.RowMaximum(), src/lu.jl:13
+    pass
+
+
+class NoPivot:      # LinearAlgebra.NoPivot(), src/lu.jl:14
+    pass
+
+
+def _normalize_pivot(pivot) -> bool:
+    """src/lu.jl:10-17: Val(true)/RowMaximum() -> True, Val(false)/NoPivot() -> False."""
+    if isinstance(pivot, (RowMaximum,)) or pivot is RowMaximum:
+        return True
+    if isinstance(pivot, (NoPivot,)) or pivot is NoPivot:
+        return False
+    if isinstance(pivot, (bool, np.bool_)):
+        return bool(pivot)
+    raise TypeError(f"pivot must be True/False, RowMaximum() or NoPivot(); got {pivot!r}")
+
+
+def nsplit(dtype, n: int) -> int:
+    """Split column of the recursion, src/lu.jl:158-162 (host logic shared with the C++ driver)."""
+    k = max(2, 128 // np.dtype(dtype).itemsize)
+    return ((n + k // 2) // k) * (k // 2) if n >= k else n // 2
+
+
+# ----------------------------------------------------------------------------------------------
+# context
+# ----------------------------------------------------------------------------------------------
+class Context:
+    """Owns one ``rfb_ctx`` (stream + device workspaces) on one GPU.  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.rfb_create(C.byref(self._h), device)
+        if rc != _lib.RFB_OK:
+            msg = self._lib.rfb_last_error(self._h).decode() if self._h else "rfb_create failed"
+            if self._h:
+                self._lib.rfb_destroy(self._h)
+                self._h = C.c_void_p()
+            raise RfbError(rc, msg)
+        self.device = device
+        self._pinned = []
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != _lib.RFB_OK:
+            raise RfbError(rc, self._lib.rfb_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for addr in getattr(self, "_pinned", []):
+                self._lib.rfb_host_free(self._h, C.c_void_p(addr))
+            self._pinned = []
+            self._lib.rfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self) -> dict:
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._check(self._lib.rfb_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "mem_bytes": mem.value}
+
+    def sync(self):
+        self._check(self._lib.rfb_sync(self._h))
+
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.rfb_malloc(self._h, C.byref(p), nbytes))
+        return p.value
+
+    def free(self, ptr: int):
+        self._check(self._lib.rfb_free(self._h, C.c_void_p(ptr)))
+
+    def pinned_empty(self, shape, dtype, order="F") -> np.ndarray:
+        """numpy array over page-locked host memory (cudaHostAlloc); released when the context closes."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self._lib.rfb_host_alloc(self._h, C.byref(p), max(n, 16)))
+        buf = (C.c_byte * max(n, 16)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape, order=order)
+        self._pinned.append(p.value)         # released in close()
+        return arr
+
+    def h2d(self, dst: int, src: np.ndarray):
+        self._check(self._lib.rfb_h2d(self._h, C.c_void_p(dst), C.c_void_p(src.ctypes.data), src.nbytes))
+
+    def d2h(self, dst: np.ndarray, src: int):
+        self._check(self._lib.rfb_d2h(self._h, C.c_void_p(dst.ctypes.data), C.c_void_p(src), dst.nbytes))
+
+    def d2d(self, dst: int, src: int, nbytes: int):
+        self._check(self._lib.rfb_d2d(self._h, C.c_void_p(dst), C.c_void_p(src), nbytes))
+
+    def memset(self, dst: int, value: int, nbytes: int):
+        self._check(self._lib.rfb_memset(self._h, C.c_void_p(dst), value, nbytes))
+
+    def timer_start(self):
+        self._check(self._lib.rfb_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.rfb_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        c = C.c_int64()
+        self._check(self._lib.rfb_launch_count(self._h, C.byref(c)))
+        return int(c.value)
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.rfb_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        work = (C.c_double * 8)()
+        self._check(self._lib.rfb_profile_read(self._h, ms, cnt, work))
+        names = ["panel", "laswp", "trsm_diag", "gemm", "other"]
+        return {n: {"ms": ms[i], "launches": cnt[i], "work": work[i]} for i, n in enumerate(names)}
+
+    def dmma_peak_tflops(self, iters: int = 20000) -> float:
+        v = C.c_double()
+        self._check(self._lib.rfb_bench_dmma_peak(self._h, iters, C.byref(v)))
+        return float(v.value)
+
+    def copy_gbs(self, nbytes: int = 1 << 30, iters: int = 5) -> float:
+        v = C.c_double()
+        self._check(self._lib.rfb_bench_copy(self._h, nbytes, iters, C.byref(v)))
+        return float(v.value)
+
+    # -- whole path -----------------------------------------------------------------------------
+    def lu_raw(self, a_ptr: int, m: int, n: int, lda: int, ipiv_ptr: int, info_ptr: int, dtype,
+               opts: Optional[rfb_opts] = None) -> None:
+        fn = self._lib.rfb_lu_f64 if np.dtype(dtype) == np.float64 else self._lib.rfb_lu_f32
+        self._check(fn(self._h, C.c_void_p(a_ptr), m, n, lda, C.c_void_p(ipiv_ptr), C.c_void_p(info_ptr),
+                       C.byref(opts) if opts is not None else None))
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    """Process-wide context on the GPU selected by LOCAL_RANK (one process per GPU) or device 0."""
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+# ----------------------------------------------------------------------------------------------
+# LinearAlgebra.LU
+# ----------------------------------------------------------------------------------------------
+class LU:
+    """``LinearAlgebra.LU{T,Matrix{T},Vector{Int64}}`` as returned at src/lu.jl:129.
+
+    ``factors`` holds L strictly below the diagonal (unit diagonal implied) and U on/above it;
+    ``ipiv`` is 1-based sequential-swap; ``info`` 0 or the first zero-pivot column.
+    """
+
+    def __init__(self, factors: np.ndarray, ipiv: np.ndarray, info: int):
+        self.factors, self.ipiv, self.info = factors, ipiv, int(info)
+
+    def __iter__(self):                      # Julia: L, U, p = F
+        return iter((self.L, self.U, self.p))
+
+    @property
+    def issuccess(self) -> bool:
+        return self.info == 0
+
+    @property
+    def L(self) -> np.ndarray:
+        m, n = self.factors.shape
+        mn = min(m, n)
+        out = np.tril(self.factors[:, :mn], -1)
+        out[np.arange(mn), np.arange(mn)] = 1
+        return out
+
+    @property
+    def U(self) -> np.ndarray:
+        m, n = self.factors.shape
+        return np.triu(self.factors[:min(m, n), :])
+
+    @property
+    def p(self) -> np.ndarray:
+        """0-based row permutation with ``A[p, :] == L @ U`` (Julia's ``F.p`` minus one)."""
+        m = self.factors.shape[0]
+        p = np.arange(m)
+        for i, ip in enumerate(self.ipiv):
+            ip = int(ip) - 1
+            if ip != i:
+                p[i], p[ip] = p[ip], p[i]
+        return p
+
+    @property
+    def P(self) -> np.ndarray:
+        m = self.factors.shape[0]
+        out = np.zeros((m, m), dtype=self.factors.dtype)
+        out[np.arange(m), self.p] = 1
+        return out
+
+    def __repr__(self):
+        return f"LU(factors={self.factors.shape} {self.factors.dtype}, info={self.info})"
+
+
+# ----------------------------------------------------------------------------------------------
+# lu / lu!
+# ----------------------------------------------------------------------------------------------
+def _make_opts(mem_space=_lib.RFB_MEM_HOST, leaf_width=0, f32_mode=0, trsm_block=0, gemm_path=0,
+               laswp_path=0) -> rfb_opts:
+    o = rfb_opts()
+    o.mem_space, o.leaf_width, o.f32_mode = mem_space, leaf_width, f32_mode
+    o.trsm_block, o.gemm_path, o.laswp_path = trsm_block, gemm_path, laswp_path
+    return o
+
+
+def lu_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check=True,
+        blocksize: Optional[int] = None, threshold: Optional[int] = None, ctx: Optional[Context] = None,
+        leaf_width: int = 0, f32_mode: int = 0, trsm_block: int = 0, gemm_path: int = 0,
+        laswp_path: int = 0) -> LU:
+    """``RecursiveFactorization.lu!`` (src/lu.jl:67-83 and :97-130): factor ``A`` in place.
+
+    ``A`` must be a column-major float64/float32 matrix (it is overwritten with L\\U and returned
+    inside the ``LU``); ``ipiv``, if given, must be an int64 vector of length ``min(m, n)`` and is
+    the one returned.  ``thread`` is accepted and ignored (the GPU is always "threaded");
+    ``blocksize``/``threshold`` tune the reference's CPU register kernel and are accepted and
+    ignored -- the analogous GPU knob is ``leaf_width``.  ``check=True`` raises
+    ``SingularException`` when ``info > 0`` like ``checknonsingular`` (src/lu.jl:128).
+    """
+    if not _normalize_pivot(pivot):
+        raise NotImplementedError(
+            "pivot=Val(false)/NoPivot() (src/lu.jl:27-65) is outside the B200 hot path; no fallback is provided")
+    if not isinstance(A, np.ndarray) or A.ndim != 2:
+        raise TypeError("A must be a 2-D numpy array")
+    if A.dtype not in (np.float64, np.float32):
+        raise TypeError(f"eltype {A.dtype} is not supported on the B200 path (Float64/Float32 only); no fallback")
+    m, n = A.shape
+    if not (A.flags.f_contiguous or m <= 1 or n <= 1) or not A.flags.writeable or not A.flags.aligned:
+        raise TypeError("lu_ factors in place and needs a writeable column-major (Fortran-ordered) array; "
+                        "use lu() to factor a copy of any layout")
+    mn = min(m, n)
+    if ipiv is None:
+        ipiv = np.empty(mn, dtype=np.int64)                     # init_pivot, src/lu.jl:40
+    else:
+        if not isinstance(ipiv, np.ndarray) or ipiv.dtype != np.int64 or ipiv.ndim != 1 or \
+                not ipiv.flags.c_contiguous:
+            raise TypeError("ipiv must be a contiguous int64 vector (Vector{BlasInt})")
+        if ipiv.size != mn:
+            raise ValueError(f"ipiv has length {ipiv.size}, expected min(m, n) = {mn}")
+    ctx = ctx or default_context()
+    info = C.c_int64(0)
+    lda = max(m, 1) if A.flags.f_contiguous else max(m, 1)
+    opts = _make_opts(_lib.RFB_MEM_HOST, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path)
+    ctx.lu_raw(A.ctypes.data if A.size else 0, m, n, lda, ipiv.ctypes.data if mn else 0, C.addressof(info),
+               A.dtype, opts)
+    if check and info.value > 0:
+        raise SingularException(info.value)
+    return LU(A, ipiv, info.value)
+
+
+def lu(A, pivot=True, thread=False, **kwargs) -> LU:
+    """``RecursiveFactorization.lu`` (src/lu.jl:19-21): ``lu!(copy(A), ...)``."""
+    A = np.asarray(A)
+    if A.ndim != 2:
+        raise TypeError("A must be a matrix")
+    return lu_(np.array(A, order="F", copy=True), None, pivot, thread, **kwargs)
+
+
+# ----------------------------------------------------------------------------------------------
+# device-resident use (inputs already in HBM): what the roofline numbers are measured on
+# ----------------------------------------------------------------------------------------------
+class DeviceMatrix:
+    """A column-major matrix + pivot vector + info word living in device memory."""
+
+    def __init__(self, ctx: Context, m: int, n: int, dtype, lda: Optional[int] = None):
+        self.ctx, self.m, self.n, self.dtype = ctx, m, n, np.dtype(dtype)
+        self.lda = lda if lda is not None else max((m + 1) & ~1, 2)
+        self.nbytes = self.lda * max(n, 1) * self.dtype.itemsize
+        self.ptr = ctx.malloc(self.nbytes)
+        self.ipiv_ptr = ctx.malloc(max(min(m, n), 1) * 8)
+        self.info_ptr = ctx.malloc(64)
+
+    def upload(self, a: np.ndarray):
+        assert a.shape == (self.m, self.n) and a.dtype == self.dtype
+        if self.lda == self.m and a.flags.f_contiguous:
+            self.ctx.h2d(self.ptr, a)
+        else:
+            staged = np.zeros((self.lda, self.n), dtype=self.dtype, order="F")
+            staged[: self.m, :] = a
+            self.ctx.h2d(self.ptr, staged)
+            self.ctx.sync()
+
+    def download(self):
+        staged = np.empty((self.lda, self.n), dtype=self.dtype, order="F")
+        ipiv = np.empty(min(self.m, self.n), dtype=np.int64)
+        info = np.zeros(8, dtype=np.int64)
+        self.ctx.d2h(staged, self.ptr)
+        if ipiv.size:
+            self.ctx.d2h(ipiv, self.ipiv_ptr)
+        self.ctx.d2h(info[:1], self.info_ptr)
+        self.ctx.sync()
+        return np.asfortranarray(staged[: self.m, :]), ipiv, int(info[0])
+
+    def copy_from(self, other: "DeviceMatrix"):
+        assert other.nbytes == self.nbytes
+        self.ctx.d2d(self.ptr, other.ptr, self.nbytes)
+
+    def lu(self, **opt_kw):
+        """Enqueue the factorization where the matrix lies (no copies, no sync)."""
+        opts = _make_opts(_lib.RFB_MEM_DEVICE, **opt_kw)
+        self.ctx.lu_raw(self.ptr, self.m, self.n, self.lda, self.ipiv_ptr, self.info_ptr, self.dtype, opts)
+
+    def free(self):
+        for p in (self.ptr, self.ipiv_ptr, self.info_ptr):
+            if p:
+                self.ctx.free(p)
+        self.ptr = self.ipiv_ptr = self.info_ptr = 0

@@ -1,0 +1,303 @@
+// panel_impl.cuh -- K1: pivoted LU of a tall m x n panel (n <= 64) in ONE launch.
+//
+// Replaces the reference's leaf `_generic_lufact!` (src/lu.jl:290-338) *and* the bottom levels of
+// `reckernel!` (src/lu.jl:189-263) whose nodes are narrower than the leaf width: the result is the
+// same factorization (first-strict-max pivot :296-305, reciprocal scaling :317-320, info rule
+// :321-327, rank-1 updates :330-334) with LAPACK sequential-swap pivots.
+//
+// B200 design (not a translation of the CPU loop nest):
+//   * rows are distributed over the CTAs of a cooperative grid, ONE ROW PER THREAD, and the whole
+//     row (n <= 64 values) lives in registers for the entire panel: the panel is read from HBM
+//     once and written once (algorithmic bytes 2*s*m*n), every rank-1 update is register FMAs;
+//   * implicit pivoting: rows never move during the panel.  Each thread tracks the LOGICAL
+//     position its row would have under LAPACK's sequential swaps (`logpos`); the argmax tie-break
+//     uses the logical position, so pivots are bit-identical to the swapping algorithm; rows are
+//     scattered to their final position in the single write-back at the end;
+//   * one exchange per column and NO grid barrier: each CTA reduces its candidate with warp
+//     shuffles, the winning thread publishes {|v|, logpos} and its row to a per-CTA slot in L2
+//     (every 16-byte word carries its epoch tag, so readers just poll for the tag; two parities
+//     make the slots reusable without a second sync); every CTA then reduces the G headers
+//     redundantly and reads the winner's row.
+#include <cooperative_groups.h>
+
+#include "rfb_internal.h"
+
+namespace {
+
+constexpr unsigned int kNone = 0xFFFFFFFFu;
+constexpr unsigned int kSpinLimit = 1u << 22;
+
+__device__ __forceinline__ void st_xchg(ulonglong2 *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_xchg(const ulonglong2 *p) {
+    ulonglong2 r;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
+    unsigned int r;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long to_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ unsigned long long to_bits(float v) { return (unsigned long long)__float_as_uint(v); }
+template <typename T> __device__ __forceinline__ T from_bits(unsigned long long b);
+template <> __device__ __forceinline__ double from_bits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+template <> __device__ __forceinline__ float from_bits<float>(unsigned long long b) { return __uint_as_float((unsigned int)b); }
+__device__ __forceinline__ double rcp_rn(double v) { return __drcp_rn(v); }
+__device__ __forceinline__ float rcp_rn(float v) { return __frcp_rn(v); }
+
+// Candidate ordering of src/lu.jl:299-304: larger |v| wins; among equal |v| the FIRST (lowest
+// logical row) wins.  key == 0 encodes "not greater than the initial amax = 0" (zeros and NaNs).
+struct Cand {
+    unsigned long long key;
+    unsigned int lp;
+    unsigned int src;
+};
+__device__ __forceinline__ bool better(unsigned long long k1, unsigned int lp1, unsigned long long k2, unsigned int lp2) {
+    return k1 > k2 || (k1 == k2 && lp1 < lp2);
+}
+__device__ __forceinline__ Cand warp_best(Cand c) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long ok = __shfl_xor_sync(0xffffffffu, c.key, off);
+        unsigned int olp = __shfl_xor_sync(0xffffffffu, c.lp, off);
+        unsigned int os = __shfl_xor_sync(0xffffffffu, c.src, off);
+        if (better(ok, olp, c.key, c.lp)) { c.key = ok; c.lp = olp; c.src = os; }
+    }
+    return c;
+}
+
+template <int WARPS>
+struct ReduceBuf {
+    unsigned long long key[WARPS];
+    unsigned int lp[WARPS];
+    unsigned int src[WARPS];
+};
+
+// One __syncthreads.  Every thread returns the block-wide best candidate.
+template <int WARPS>
+__device__ __forceinline__ Cand block_best(Cand c, ReduceBuf<WARPS> &buf, int warp, int lane) {
+    c = warp_best(c);
+    if (lane == 0) { buf.key[warp] = c.key; buf.lp[warp] = c.lp; buf.src[warp] = c.src; }
+    __syncthreads();
+    Cand b{buf.key[0], buf.lp[0], buf.src[0]};
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+        unsigned long long k = buf.key[w];
+        unsigned int l = buf.lp[w];
+        if (better(k, l, b.key, b.lp)) { b.key = k; b.lp = l; b.src = buf.src[w]; }
+    }
+    return b;
+}
+
+template <typename T, int NB, int WARPS>
+struct PanelShared {
+    T u[2][NB];
+    ReduceBuf<WARPS> loc[2];
+    ReduceBuf<WARPS> glb[2];
+};
+
+struct PanelArgs {
+    int n, G, bid, tid, lane, warp;
+    long long *ipiv;
+    long long ipiv_add;
+    long long *info;
+    long long col_offset;
+    RfbPanelXchg *x;
+    unsigned int epoch_base;
+};
+
+// Column step K of the panel.  K is a template parameter (and the steps are chained by template
+// recursion, not a loop) so that every index into the per-thread row `reg` is a compile-time
+// constant and the row provably stays in registers.
+template <typename T, int NB, int THREADS, int K>
+__device__ __forceinline__ void panel_steps(T (&reg)[NB], bool &alive, unsigned int &logpos, int &finalpos,
+                                            bool &bailed, PanelShared<T, NB, THREADS / 32> &sh,
+                                            const PanelArgs &pa) {
+    if constexpr (K < NB) {
+        constexpr int WARPS = THREADS / 32;
+        if (K >= pa.n) return;
+        constexpr int par = K & 1;
+        const unsigned int epoch = pa.epoch_base + (unsigned int)K;
+        const int tid = pa.tid, bid = pa.bid, n = pa.n;
+        RfbPanelXchg *x = pa.x;
+
+        // -- local candidate (src/lu.jl:296-305) ------------------------------------------------
+        const T av = fabs(reg[K]);
+        Cand c;
+        c.key = (alive && av > T(0)) ? to_bits(av) : 0ull;
+        c.lp = alive ? logpos : kNone;
+        c.src = (unsigned int)bid;
+        const Cand cb = block_best<WARPS>(c, sh.loc[par], pa.warp, pa.lane);
+        const bool cta_winner = alive && logpos == cb.lp;
+
+        Cand wb;
+        if (pa.G == 1) {
+            wb = cb;
+            if (cta_winner) {
+#pragma unroll
+                for (int j = K; j < NB; ++j) sh.u[par][j] = reg[j];
+            }
+            __syncthreads();
+        } else {
+            // -- publish this CTA's candidate and its row -------------------------------------
+            if (cta_winner) {
+#pragma unroll
+                for (int j = K; j < NB; ++j)
+                    if (j < n) st_xchg(&x->row[par][bid][j], to_bits(reg[j]), (unsigned long long)epoch);
+                st_xchg(&x->header[par][bid], cb.key, ((unsigned long long)epoch << 32) | cb.lp);
+            } else if (cb.lp == kNone && tid == 0) {
+                st_xchg(&x->header[par][bid], 0ull, ((unsigned long long)epoch << 32) | kNone);
+            }
+            // -- gather all G headers, reduce redundantly in every CTA ------------------------
+            Cand g{0ull, kNone, 0u};
+            for (int cta = tid; cta < pa.G; cta += THREADS) {
+                ulonglong2 h;
+                unsigned int spins = 0;
+                while (true) {
+                    h = ld_xchg(&x->header[par][cta]);
+                    if ((unsigned int)(h.y >> 32) == epoch) break;
+                    if (bailed) break;
+                    if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
+                        atomicExch(&x->error_flag, 1u);
+                        bailed = true;
+                        break;
+                    }
+                }
+                const unsigned int hl = (unsigned int)h.y;
+                if (better(h.x, hl, g.key, g.lp)) { g.key = h.x; g.lp = hl; g.src = (unsigned int)cta; }
+            }
+            wb = block_best<WARPS>(g, sh.glb[par], pa.warp, pa.lane);
+            // -- fetch the winning row --------------------------------------------------------
+            if (tid >= K && tid < n) {
+                ulonglong2 d;
+                unsigned int spins = 0;
+                while (true) {
+                    d = ld_xchg(&x->row[par][wb.src][tid]);
+                    if ((unsigned int)d.y == epoch) break;
+                    if (bailed) break;
+                    if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
+                        atomicExch(&x->error_flag, 1u);
+                        bailed = true;
+                        break;
+                    }
+                }
+                sh.u[par][tid] = from_bits<T>(d.x);
+            }
+            __syncthreads();
+        }
+
+        // -- eliminate (src/lu.jl:307-334) ------------------------------------------------------
+        const T pv = sh.u[par][K];
+        if (alive && logpos == wb.lp) {
+            alive = false;            // this row is pivot row K: frozen from now on
+            finalpos = K;
+        } else if (alive) {
+            if (logpos == (unsigned int)K) logpos = wb.lp;   // the swap K <-> kp, done on the index
+            T l = reg[K];
+            if (pv != T(0)) l *= rcp_rn(pv);                 // reciprocal scaling (:317-320)
+            reg[K] = l;
+            const T nl = -l;
+#pragma unroll
+            for (int j = K + 1; j < NB; ++j) reg[j] = fma(nl, sh.u[par][j], reg[j]);
+        }
+        if (bid == 0 && tid == 0) {
+            pa.ipiv[K] = (long long)wb.lp + 1 + pa.ipiv_add;
+            if (pv == T(0) && *pa.info == 0) *pa.info = pa.col_offset + K + 1;   // (:321-327)
+        }
+        panel_steps<T, NB, THREADS, K + 1>(reg, alive, logpos, finalpos, bailed, sh, pa);
+    }
+}
+
+template <typename T, int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ ipiv,
+             long long ipiv_add, long long *__restrict__ info, long long col_offset,
+             RfbPanelXchg *__restrict__ x, unsigned int epoch_base) {
+    __shared__ PanelShared<T, NB, THREADS / 32> sh;
+    PanelArgs pa;
+    pa.n = n; pa.G = gridDim.x; pa.bid = blockIdx.x; pa.tid = threadIdx.x;
+    pa.lane = threadIdx.x & 31; pa.warp = threadIdx.x >> 5;
+    pa.ipiv = ipiv; pa.ipiv_add = ipiv_add; pa.info = info; pa.col_offset = col_offset;
+    pa.x = x; pa.epoch_base = epoch_base;
+    const int row = pa.bid * THREADS + pa.tid;
+
+    bool alive = row < m;
+    unsigned int logpos = (unsigned int)row;
+    int finalpos = 0;
+    bool bailed = false;
+
+    T reg[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) reg[j] = (alive && j < n) ? A[row + (long long)j * lda] : T(0);
+    if (pa.tid < NB) { sh.u[0][pa.tid] = T(0); sh.u[1][pa.tid] = T(0); }
+    __syncthreads();
+
+    panel_steps<T, NB, THREADS, 0>(reg, alive, logpos, finalpos, bailed, sh, pa);
+
+    // -- single write-back, rows land at their final (swapped) position --------------------------
+    if (row < m) {
+        const long long dst = alive ? (long long)logpos : (long long)finalpos;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+            if (j < n) A[dst + (long long)j * lda] = reg[j];
+    }
+}
+
+template <typename T, int NB, int THREADS>
+int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
+                      int64_t *info, int64_t col_offset, int G) {
+    auto kern = panel_kernel<T, NB, THREADS>;
+    long long lda_ = lda, add_ = ipiv_add, off_ = col_offset;
+    long long *ipiv_ = (long long *)ipiv, *info_ = (long long *)info;
+    RfbPanelXchg *x = ctx->xchg;
+    unsigned int epoch = ctx->panel_epoch;
+    void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch};
+    RfbLaunchScope scope(ctx, RFB_KC_PANEL, (double)m * n * n - (double)n * n * n / 3.0);
+    if (G == 1) {
+        RFB_CUDA(ctx, cudaLaunchKernel((const void *)kern, dim3(1), dim3(THREADS), args, 0, ctx->stream));
+    } else {
+        RFB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(THREADS), args, 0, ctx->stream));
+    }
+    return RFB_OK;
+}
+
+template <typename T, int THREADS>
+int launch_panel_threads(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
+                         int64_t *info, int64_t col_offset, int G) {
+    if (n <= 16) return launch_panel_inst<T, 16, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G);
+    if (n <= 32) return launch_panel_inst<T, 32, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G);
+    return launch_panel_inst<T, 64, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G);
+}
+
+}  // namespace
+
+template <typename T>
+int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
+                     int64_t ipiv_add, int64_t *info_dev, int64_t col_offset) {
+    if (n <= 0 || m <= 0) return RFB_OK;
+    if (n > RFB_MAX_NB) return ctx->fail(RFB_ERR_UNSUPPORTED, "panel width %lld > %d", (long long)n, RFB_MAX_NB);
+    if (m < n) return ctx->fail(RFB_ERR_ARG, "panel needs m >= n (got %lld x %lld)", (long long)m, (long long)n);
+    // epoch hygiene: tags are 32 bit; restart the sequence (and wipe stale tags) long before wrap
+    if (ctx->panel_epoch > 0xF0000000u) {
+        RFB_CUDA(ctx, cudaMemsetAsync(ctx->xchg, 0, sizeof(RfbPanelXchg), ctx->stream));
+        ctx->panel_epoch = 1;
+    }
+    const int max_ctas = ctx->sm_count < RFB_MAX_PANEL_CTAS ? ctx->sm_count : RFB_MAX_PANEL_CTAS;
+    int rc;
+    const int64_t g128 = (m + 127) / 128, g256 = (m + 255) / 256;
+    if (g128 <= max_ctas)
+        rc = launch_panel_threads<T, 128>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g128);
+    else if (g256 <= max_ctas)
+        rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256);
+    else
+        return ctx->fail(RFB_ERR_UNSUPPORTED, "panel with %lld rows exceeds one-row-per-thread capacity (%d)",
+                         (long long)m, max_ctas * 256);
+    ctx->panel_epoch += (unsigned int)n;
+    return rc;
+}
+
+template int rfb_launch_panel<RFB_PANEL_T>(rfb_ctx *, RFB_PANEL_T *, int64_t, int64_t, int64_t, int64_t *, int64_t, int64_t *, int64_t);

@@ -1,0 +1,381 @@
+// rfb_api.cu -- C ABI entry points, context management and the host-side recursion.
+//
+// The recursion is a twin of the reference driver: lu! (src/lu.jl:97-130), _recurse! with its fat
+// tail (:145-156) and reckernel! (:189-263).  Differences that do not change the result:
+//   * pivots and info are produced in GLOBAL coordinates by the kernels, so the reference's
+//     `P2 .+= n1` (:256-260) and `info += n1` (:248-255) fix-ups have nothing left to do;
+//   * recursion stops at `leaf_width` columns (default 64) instead of blocksize 8/16 (:101): one
+//     K1 launch factors the whole leaf panel.
+#include <cstdarg>
+
+#include "rfb_internal.h"
+
+int rfb_ctx::fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error = buf;
+    return code;
+}
+
+namespace {
+
+struct LuPlan {
+    int leaf;
+    const rfb_opts *opts;
+};
+
+// reckernel! (src/lu.jl:189-263) on columns [c0, c0 + n) of the root matrix; the node's block is
+// rows [c0, m) (the diagonal block starts at row c0 == column c0).
+template <typename T>
+int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
+           const LuPlan &plan) {
+    T *A = root + c0 + c0 * lda;          // top-left of the node
+    const int64_t mm = m - c0;            // rows of the node
+    if (n <= plan.leaf)                   // :192-195 leaf -> K1
+        return rfb_launch_panel<T>(ctx, A, mm, n, lda, ipiv + c0, c0, info, c0);
+    const int64_t n1 = rfb_nsplit<T>(n), n2 = n - n1;                                   // :196-198
+    RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n1, ipiv, info, plan));                    // :229
+    T *AR = A + n1 * lda;
+    RFB_TRY(rfb_launch_laswp<T>(ctx, AR, n2, lda, ipiv + c0, n1, c0));                  // :233
+    RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
+    RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
+    RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan));               // :244
+    return rfb_launch_laswp<T>(ctx, A + n1, n1, lda, ipiv + c0 + n1, n2, c0 + n1);      // :246
+}
+
+template <typename T>
+int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d_ipiv, int64_t *d_info,
+              const rfb_opts *opts) {
+    LuPlan plan;
+    plan.opts = opts;
+    plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
+    if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
+        return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
+    RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t), ctx->stream));
+    const int64_t mn = m < n ? m : n;
+    if (mn == 0) return RFB_OK;
+    RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan));                   // :147
+    if (m < n) {                                                                        // :148-154
+        T *AR = dA + m * lda;
+        RFB_TRY(rfb_launch_laswp<T>(ctx, AR, n - m, lda, d_ipiv, mn, 0));
+        RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
+    }
+    return RFB_OK;
+}
+
+template <typename T>
+int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
+             const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (m < 0 || n < 0) return ctx->fail(RFB_ERR_ARG, "negative dimension (%lld x %lld)", (long long)m, (long long)n);
+    if (lda < (m > 1 ? m : 1)) return ctx->fail(RFB_ERR_ARG, "lda %lld < max(1, m) with m = %lld", (long long)lda, (long long)m);
+    if (!info) return ctx->fail(RFB_ERR_ARG, "info is null");
+    const int64_t mn = m < n ? m : n;
+    if (mn > 0 && (!A || !ipiv)) return ctx->fail(RFB_ERR_ARG, "A or ipiv is null");
+    if (m > 0x7fffffffLL || n > 0x7fffffffLL) return ctx->fail(RFB_ERR_UNSUPPORTED, "dimension exceeds int32");
+    RFB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int space = opts ? opts->mem_space : RFB_MEM_HOST;
+    if (mn == 0) {
+        if (space == RFB_MEM_HOST) *info = 0;
+        else RFB_CUDA(ctx, cudaMemsetAsync(info, 0, sizeof(int64_t), ctx->stream));
+        return RFB_OK;
+    }
+    if (space == RFB_MEM_DEVICE) return lu_device<T>(ctx, A, m, n, lda, ipiv, info, opts);
+    if (space != RFB_MEM_HOST) return ctx->fail(RFB_ERR_ARG, "unknown mem_space %d", space);
+
+    // host pointers: stage through a grow-only device buffer with a dense leading dimension
+    const int64_t ldd = (m + 1) & ~int64_t(1);          // even => 16-byte aligned columns for f64
+    const size_t need = sizeof(T) * (size_t)ldd * (size_t)n;
+    if (need > ctx->d_mat_cap) {
+        if (ctx->d_mat) cudaFree(ctx->d_mat);
+        ctx->d_mat = nullptr;
+        ctx->d_mat_cap = 0;
+        if (cudaMalloc(&ctx->d_mat, need) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the matrix", need);
+        }
+        ctx->d_mat_cap = need;
+    }
+    if ((size_t)mn > ctx->d_ipiv_cap) {
+        if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
+        ctx->d_ipiv = nullptr;
+        ctx->d_ipiv_cap = 0;
+        if (cudaMalloc(&ctx->d_ipiv, sizeof(int64_t) * (size_t)mn) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate the device pivot vector");
+        }
+        ctx->d_ipiv_cap = (size_t)mn;
+    }
+    T *dA = reinterpret_cast<T *>(ctx->d_mat);
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(dA, sizeof(T) * ldd, A, sizeof(T) * lda, sizeof(T) * m, n,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, ctx->d_ipiv, ctx->d_info, opts));
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * lda, dA, sizeof(T) * ldd, sizeof(T) * m, n,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpyAsync(ipiv, ctx->d_ipiv, sizeof(int64_t) * mn, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[0], ctx->d_info, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[1], &ctx->xchg->error_flag, sizeof(unsigned int),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *info = ctx->h_pinned[0];
+    if ((unsigned int)ctx->h_pinned[1] != 0)
+        return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+    return RFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfb_version(void) { return 100; }
+
+int rfb_create(rfb_ctx **out, int device) {
+    if (!out) return RFB_ERR_ARG;
+    *out = nullptr;
+    rfb_ctx *ctx = new rfb_ctx();
+    *out = ctx;   // returned even on failure so that rfb_last_error works; caller still destroys it
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ctx->fail(RFB_ERR_CUDA, "no CUDA device available (%s); librfb200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return ctx->fail(RFB_ERR_ARG, "device %d out of range [0, %d)", device, ndev);
+    ctx->device = device;
+    RFB_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RFB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->mem_bytes = prop.totalGlobalMem;
+    if (prop.major != 10)
+        return ctx->fail(RFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; librfb200 is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
+    RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_stop));
+    RFB_CUDA(ctx, cudaMalloc(&ctx->xchg, sizeof(RfbPanelXchg)));
+    RFB_CUDA(ctx, cudaMemset(ctx->xchg, 0, sizeof(RfbPanelXchg)));
+    RFB_CUDA(ctx, cudaMalloc(&ctx->d_info, 64));
+    RFB_CUDA(ctx, cudaMemset(ctx->d_info, 0, 64));
+    RFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_pinned, 64, cudaHostAllocDefault));
+    memset(ctx->h_pinned, 0, 64);
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        ctx->encode_tiled = nullptr;   // the TMA GEMM path then reports "not handled"
+    }
+    return RFB_OK;
+}
+
+int rfb_destroy(rfb_ctx *ctx) {
+    if (!ctx) return RFB_OK;
+    if (ctx->stream) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->xchg) cudaFree(ctx->xchg);
+    if (ctx->d_info) cudaFree(ctx->d_info);
+    if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
+    if (ctx->d_mat) cudaFree(ctx->d_mat);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return RFB_OK;
+}
+
+const char *rfb_last_error(rfb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int rfb_device_info(rfb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *mem_bytes) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+    return RFB_OK;
+}
+
+int rfb_lu_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
+               const rfb_opts *opts) {
+    return lu_entry<double>(ctx, A, m, n, lda, ipiv, info, opts);
+}
+int rfb_lu_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
+               const rfb_opts *opts) {
+    return lu_entry<float>(ctx, A, m, n, lda, ipiv, info, opts);
+}
+
+#define RFB_CHECK_CTX(ctx) \
+    if (!(ctx)) return RFB_ERR_ARG
+
+int rfb_panel_getrf_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
+                        int64_t ipiv_add, int64_t *info_dev, int64_t col_offset) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_panel<double>(ctx, A, m, n, lda, ipiv_dev, ipiv_add, info_dev, col_offset);
+}
+int rfb_panel_getrf_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
+                        int64_t ipiv_add, int64_t *info_dev, int64_t col_offset) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_panel<float>(ctx, A, m, n, lda, ipiv_dev, ipiv_add, info_dev, col_offset);
+}
+int rfb_laswp_f64(rfb_ctx *ctx, double *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev, int64_t npiv,
+                  int64_t ipiv_sub) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_laswp<double>(ctx, A, ncols, lda, ipiv_dev, npiv, ipiv_sub);
+}
+int rfb_laswp_f32(rfb_ctx *ctx, float *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev, int64_t npiv,
+                  int64_t ipiv_sub) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_laswp<float>(ctx, A, ncols, lda, ipiv_dev, npiv, ipiv_sub);
+}
+int rfb_trsm_llnu_f64(rfb_ctx *ctx, const double *L, int64_t k, double *B, int64_t nrhs, int64_t lda) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_trsm<double>(ctx, L, k, B, nrhs, lda, nullptr);
+}
+int rfb_trsm_llnu_f32(rfb_ctx *ctx, const float *L, int64_t k, float *B, int64_t nrhs, int64_t lda) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_trsm<float>(ctx, L, k, B, nrhs, lda, nullptr);
+}
+int rfb_gemm_nn_sub_f64(rfb_ctx *ctx, double *C, const double *A, const double *B, int64_t m, int64_t n,
+                        int64_t k, int64_t lda) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_gemm<double>(ctx, C, A, B, m, n, k, lda, nullptr);
+}
+int rfb_gemm_nn_sub_f32(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m, int64_t n, int64_t k,
+                        int64_t lda) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_gemm<float>(ctx, C, A, B, m, n, k, lda, nullptr);
+}
+int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_ipiv_shift(ctx, ipiv_dev, n, shift);
+}
+
+int rfb_malloc(rfb_ctx *ctx, void **dev_ptr, size_t bytes) {
+    RFB_CHECK_CTX(ctx);
+    if (!dev_ptr) return ctx->fail(RFB_ERR_ARG, "dev_ptr is null");
+    *dev_ptr = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(dev_ptr, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(RFB_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+    }
+    return RFB_OK;
+}
+int rfb_free(rfb_ctx *ctx, void *dev_ptr) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaFree(dev_ptr));
+    return RFB_OK;
+}
+int rfb_host_alloc(rfb_ctx *ctx, void **host_ptr, size_t bytes) {
+    RFB_CHECK_CTX(ctx);
+    if (!host_ptr) return ctx->fail(RFB_ERR_ARG, "host_ptr is null");
+    *host_ptr = nullptr;
+    if (cudaHostAlloc(host_ptr, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(RFB_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    }
+    return RFB_OK;
+}
+int rfb_host_free(rfb_ctx *ctx, void *host_ptr) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaFreeHost(host_ptr));
+    return RFB_OK;
+}
+int rfb_h2d(rfb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return RFB_OK;
+}
+int rfb_d2h(rfb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return RFB_OK;
+}
+int rfb_d2d(rfb_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return RFB_OK;
+}
+int rfb_memset(rfb_ctx *ctx, void *dst_dev, int value, size_t bytes) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+    return RFB_OK;
+}
+int rfb_sync(rfb_ctx *ctx) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned int flag = 0;
+    RFB_CUDA(ctx, cudaMemcpy(&flag, &ctx->xchg->error_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag) return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+    return RFB_OK;
+}
+
+int rfb_timer_start(rfb_ctx *ctx) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return RFB_OK;
+}
+int rfb_timer_stop(rfb_ctx *ctx, float *ms) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    RFB_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+    float t = 0;
+    RFB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev_start, ctx->ev_stop));
+    if (ms) *ms = t;
+    return RFB_OK;
+}
+int rfb_launch_count(rfb_ctx *ctx, int64_t *count) {
+    RFB_CHECK_CTX(ctx);
+    if (count) *count = ctx->launches;
+    return RFB_OK;
+}
+int rfb_profile_enable(rfb_ctx *ctx, int on) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    ctx->prof_classes.clear();
+    for (int i = 0; i < RFB_KC_COUNT; ++i) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; ctx->prof_work[i] = 0; }
+    ctx->profiling = on != 0;
+    return RFB_OK;
+}
+int rfb_profile_read(rfb_ctx *ctx, double ms_by_class[8], int64_t launches_by_class[8], double work_by_class[8]) {
+    RFB_CHECK_CTX(ctx);
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->prof_classes.size(); ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]);
+        ctx->prof_ms[ctx->prof_classes[i]] += t;
+        cudaEventDestroy(ctx->prof_events[2 * i]);
+        cudaEventDestroy(ctx->prof_events[2 * i + 1]);
+    }
+    ctx->prof_events.clear();
+    ctx->prof_classes.clear();
+    for (int i = 0; i < RFB_KC_COUNT; ++i) {
+        if (ms_by_class) ms_by_class[i] = ctx->prof_ms[i];
+        if (launches_by_class) launches_by_class[i] = ctx->prof_launches[i];
+        if (work_by_class) work_by_class[i] = ctx->prof_work[i];
+    }
+    return RFB_OK;
+}
+int rfb_bench_dmma_peak(rfb_ctx *ctx, int iters, double *tflops) {
+    RFB_CHECK_CTX(ctx);
+    if (!tflops) return ctx->fail(RFB_ERR_ARG, "tflops is null");
+    return rfb_run_dmma_peak(ctx, iters, tflops);
+}
+int rfb_bench_copy(rfb_ctx *ctx, size_t bytes, int iters, double *gbs) {
+    RFB_CHECK_CTX(ctx);
+    if (!gbs) return ctx->fail(RFB_ERR_ARG, "gbs is null");
+    return rfb_run_copy_bench(ctx, bytes, iters, gbs);
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// rfb_internal.h -- shared declarations of librfb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <set>
+
+#include "../../include/rfb200.h"
+
+// ---------------------------------------------------------------------------------------------
+// Panel exchange workspace (K1).  One slot per CTA and step parity.  Every 16-byte word carries
+// its own epoch tag, so a reader never needs a fence: it polls until the tag matches.
+// ---------------------------------------------------------------------------------------------
+constexpr int RFB_MAX_PANEL_CTAS = 296;   // 148 SMs x 2
+constexpr int RFB_MAX_NB = 64;            // widest panel one launch factors
+
+struct RfbPanelXchg {
+    // header[parity][cta] = { |candidate| bits , (epoch << 32) | logical row }
+    ulonglong2 header[2][RFB_MAX_PANEL_CTAS];
+    // row[parity][cta][j] = { candidate row value in column j (raw bits) , epoch }
+    ulonglong2 row[2][RFB_MAX_PANEL_CTAS][RFB_MAX_NB];
+    unsigned int error_flag;              // set by a kernel whose poll loop gave up
+    unsigned int pad[3];
+};
+
+enum RfbKernelClass { RFB_KC_PANEL = 0, RFB_KC_LASWP = 1, RFB_KC_TRSM = 2, RFB_KC_GEMM = 3, RFB_KC_OTHER = 4, RFB_KC_COUNT = 8 };
+
+struct rfb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t mem_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::string last_error;
+
+    // workspaces
+    RfbPanelXchg *xchg = nullptr;         // device
+    uint32_t panel_epoch = 1;             // next unused epoch (host mirror)
+    int64_t *d_ipiv = nullptr;            // device pivots for HOST mem_space calls
+    size_t d_ipiv_cap = 0;
+    int64_t *d_info = nullptr;            // device info word
+    void *d_mat = nullptr;                // device matrix for HOST mem_space calls (grow-only)
+    size_t d_mat_cap = 0;
+    int64_t *h_pinned = nullptr;          // pinned scratch (info + small results)
+
+    // statistics
+    int64_t launches = 0;
+    bool profiling = false;
+    double prof_ms[RFB_KC_COUNT] = {0};
+    int64_t prof_launches[RFB_KC_COUNT] = {0};
+    double prof_work[RFB_KC_COUNT] = {0};  // algorithmic flops (panel, trsm, gemm) or bytes (laswp)
+    std::vector<cudaEvent_t> prof_events; // pairs (start, stop) pending
+    std::vector<int> prof_classes;
+
+    // kernels whose dynamic shared memory limit has been raised on this device
+    std::set<const void *> smem_configured;
+
+    // TMA
+    void *encode_tiled = nullptr;         // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+
+    int fail(int code, const char *fmt, ...);
+};
+
+#define RFB_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return (ctx)->fail(RFB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__,       \
+                               __LINE__, cudaGetErrorString(e__));                            \
+    } while (0)
+
+#define RFB_TRY(expr)                      \
+    do {                                   \
+        int rc__ = (expr);                 \
+        if (rc__ != RFB_OK) return rc__;   \
+    } while (0)
+
+// Raise the dynamic shared memory limit of `func` once per context.
+static inline int rfb_ensure_smem(rfb_ctx *ctx, const void *func, size_t bytes) {
+    if (ctx->smem_configured.count(func)) return RFB_OK;
+    RFB_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->smem_configured.insert(func);
+    return RFB_OK;
+}
+
+// RAII-less profiling hooks: bracket each launch with events when profiling is on.
+struct RfbLaunchScope {
+    rfb_ctx *ctx;
+    int cls;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    RfbLaunchScope(rfb_ctx *c, int k, double work = 0.0) : ctx(c), cls(k) {
+        ctx->launches++;
+        ctx->prof_launches[cls]++;
+        ctx->prof_work[cls] += work;
+        if (ctx->profiling) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, ctx->stream);
+        }
+    }
+    ~RfbLaunchScope() {
+        if (ctx->profiling) {
+            cudaEventRecord(e1, ctx->stream);
+            ctx->prof_events.push_back(e0);
+            ctx->prof_events.push_back(e1);
+            ctx->prof_classes.push_back(cls);
+        }
+    }
+};
+
+// ---- kernel launchers (each enqueues on ctx->stream, returns RFB_* status) --------------------
+template <typename T>
+int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
+                     int64_t ipiv_add, int64_t *info_dev, int64_t col_offset);
+template <typename T>
+int rfb_launch_laswp(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
+                     int64_t npiv, int64_t ipiv_sub);
+template <typename T>
+int rfb_launch_trsm(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t lda,
+                    const rfb_opts *opts);
+template <typename T>
+int rfb_launch_gemm(rfb_ctx *ctx, T *C, const T *A, const T *B, int64_t m, int64_t n, int64_t k,
+                    int64_t lda, const rfb_opts *opts);
+int rfb_launch_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);
+int rfb_run_dmma_peak(rfb_ctx *ctx, int iters, double *tflops);
+int rfb_run_copy_bench(rfb_ctx *ctx, size_t bytes, int iters, double *gbs);
+
+// src/lu.jl:158-162
+template <typename T>
+static inline int64_t rfb_nsplit(int64_t n) {
+    int64_t k = 128 / (int64_t)sizeof(T);
+    if (k < 2) k = 2;
+    int64_t k2 = k / 2;
+    return n >= k ? ((n + k2) / k) * k2 : n / 2;
+}

@@ -1,0 +1,95 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/rfb200.h declares, the ctypes table matches the header, host-side logic agrees with the
+oracle, and argument errors / the missing-GPU case fail loudly (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rfb200
+from oracle import rf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "rfb200.h")).read()
+
+
+def declared_functions():
+    code = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(rfb_[a-z0-9_]+)\s*\(", code)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(rfb200._lib.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/rfb200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(rfb200._lib.SIGNATURES) == declared_functions()
+    assert ctypes.sizeof(rfb200.rfb_opts) == 64
+    assert rfb200._lib.load().rfb_version() >= 100
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    pkg = os.path.join(ROOT, "recursivefactorization.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "rf_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+                # no library LU/BLAS on the product path either (north_star: no cuBLAS/cuSOLVER, no Triton)
+                for banned in ("import scipy", "from scipy", "getrf(", "cublas", "cusolver", "import triton",
+                               "import torch"):
+                    assert banned not in text.lower(), (f, banned)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_nsplit_matches_oracle(dtype):
+    for n in list(range(0, 200)) + [300, 4096, 8192, 16384, 32768]:
+        assert rfb200.nsplit(dtype, n) == O.nsplit(dtype, n)
+
+
+def test_argument_errors_are_loud():
+    a = np.zeros((4, 4), order="F")
+    with pytest.raises(NotImplementedError):
+        rfb200.lu(a, False)
+    with pytest.raises(NotImplementedError):
+        rfb200.lu(a, rfb200.NoPivot())
+    with pytest.raises(TypeError):
+        rfb200.lu(a.astype(np.complex128))
+    with pytest.raises(TypeError):
+        rfb200.lu_(np.zeros((4, 4), order="C"))            # in-place needs column-major
+    with pytest.raises(ValueError):
+        rfb200.lu_(a, np.zeros(3, dtype=np.int64))         # ipiv length must be min(m, n)
+    with pytest.raises(TypeError):
+        rfb200.lu_(a, np.zeros(4, dtype=np.int32))         # Vector{BlasInt} is int64
+    with pytest.raises(TypeError):
+        rfb200.lu(a, "yes")
+
+
+def test_lu_object_properties():
+    f = np.asfortranarray(np.array([[4.0, 3.0], [0.5, 2.0]]))
+    F = rfb200.LU(f, np.array([2, 2], dtype=np.int64), 0)
+    assert np.array_equal(F.L, [[1, 0], [0.5, 1]]) and np.array_equal(F.U, [[4, 3], [0, 2]])
+    assert np.array_equal(F.p, [1, 0]) and F.issuccess
+    l, u, p = F
+    assert np.array_equal(F.P @ np.array([[1.0, 2], [3, 4]]), np.array([[3.0, 4], [1, 2]]))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly():
+    with pytest.raises(rfb200.RfbError) as ei:
+        rfb200.Context(0)
+    assert "no CPU fallback" in str(ei.value)

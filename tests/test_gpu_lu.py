@@ -1,0 +1,158 @@
+"""GPU parity tests, whole path: rfb200.lu / lu_ (C ABI rfb_lu_f64/f32 with host buffers) against the
+CPU oracle and the reference's own acceptance test (test/runtests.jl:14-68)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from scipy.linalg import lapack
+
+import rfb200
+from oracle import rf_oracle as O
+from util import assert_testlu, hutchinson_residual, rand_matrix
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from cases import CASES, make_input  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "getrf_golden.npz"))
+REF_SIZES = list(range(1, 11)) + [50, 130, 300]
+
+
+def test_native_library_is_the_one_running(ctx):
+    info = ctx.device_info()
+    assert info["cc"][0] == 10 and info["sm_count"] >= 100
+    before = ctx.launch_count()
+    rfb200.lu(np.asfortranarray(np.random.default_rng(0).random((200, 200))), ctx=ctx)
+    assert ctx.launch_count() > before                      # our kernels launched, not a fallback
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("s", REF_SIZES)
+def test_reference_sweep(ctx, dtype, s):
+    """test/runtests.jl:39-64: square, fat, tall; info equality; residual bound; singular column."""
+    rng = np.random.default_rng([12, s, np.dtype(dtype).itemsize])
+    for (m, n) in ((s, s), (s, s + 2), (s + 2, s)):
+        a0 = rand_matrix(rng, m, n, dtype)
+        _, want_p, want_info = O.lu_c(a0.copy(order="F"))
+        F = rfb200.lu(a0, ctx=ctx)
+        assert_testlu(a0, F.factors, F.ipiv, F.info, want_info)
+        assert np.array_equal(F.ipiv, want_p)               # north_star: pivot indices bit-exact
+        a1 = a0.copy(order="F")
+        i = int(rng.integers(0, min(m, n)))
+        a1[:, i] = 0
+        _, want_p, want_info = O.lu_c(a1.copy(order="F"))
+        F = rfb200.lu(a1, rfb200.RowMaximum(), check=False, ctx=ctx)
+        assert F.info == want_info and F.info > 0
+        assert np.array_equal(F.ipiv, want_p)
+        with pytest.raises(rfb200.SingularException):
+            rfb200.lu(a1, ctx=ctx)                           # check=true -> checknonsingular (src/lu.jl:128)
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_golden_lapack(ctx, idx):
+    name, m, n, dt, special = CASES[idx]
+    a0 = make_input(idx)
+    F = rfb200.lu(a0, check=False, ctx=ctx)
+    assert F.info == int(GOLDEN[name + "__info"])
+    assert np.array_equal(F.ipiv, GOLDEN[name + "__ipiv"])
+    tol = 50 * max(m, n) * np.finfo(a0.dtype).eps
+    du = GOLDEN[name + "__diagu"]
+    scale = max(1.0, float(np.abs(du).max()))
+    assert np.allclose(np.diag(F.factors), du, rtol=0, atol=tol * scale)
+    if name + "__lu" in GOLDEN.files:
+        assert np.allclose(F.factors, GOLDEN[name + "__lu"], rtol=0, atol=tol * scale)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(64, 64), (65, 65), (127, 200), (200, 127), (500, 500), (1000, 1000), (1111, 1013),
+                                   (2048, 2048), (3000, 1000), (1000, 3000)])
+def test_shapes_match_oracle(ctx, dtype, shape):
+    m, n = shape
+    rng = np.random.default_rng([21, m, n])
+    a0 = rand_matrix(rng, m, n, dtype)
+    want_f, want_p, want_info = O.lu_c(a0.copy(order="F"), threads=8)
+    F = rfb200.lu(a0, ctx=ctx)
+    assert F.info == want_info == 0
+    assert np.array_equal(F.ipiv, want_p)
+    assert_testlu(a0, F.factors, F.ipiv, F.info, 0)
+    scale = max(1.0, float(np.abs(want_f).max()))
+    assert np.allclose(F.factors, want_f, rtol=0, atol=200 * max(m, n) * np.finfo(dtype).eps * scale)
+
+
+@pytest.mark.parametrize("leaf", [16, 32, 64])
+def test_leaf_width_option(ctx, leaf):
+    a0 = rand_matrix(np.random.default_rng(leaf), 700, 700, np.float64)
+    _, want_p, _ = O.lu_c(a0.copy(order="F"))
+    F = rfb200.lu(a0, ctx=ctx, leaf_width=leaf)
+    assert np.array_equal(F.ipiv, want_p)
+    assert_testlu(a0, F.factors, F.ipiv, F.info, 0)
+
+
+def test_inplace_semantics_and_user_ipiv(ctx):
+    """lu!(A, ipiv) (README.md:29): A is overwritten, the caller's ipiv is the one returned."""
+    a0 = rand_matrix(np.random.default_rng(1), 333, 333, np.float64)
+    a = a0.copy(order="F")
+    ipiv = np.full(333, -7, dtype=np.int64)
+    F = rfb200.lu_(a, ipiv, True, True, ctx=ctx)             # thread=Val(true) accepted and ignored
+    assert F.factors is a and F.ipiv is ipiv
+    assert ipiv.min() >= 1 and not np.array_equal(a, a0)
+    assert_testlu(a0, a, ipiv, F.info, 0)
+    b = a0.copy(order="F")
+    rfb200.lu(b, ctx=ctx)
+    assert np.array_equal(b, a0)                             # lu() factors a copy
+
+
+def test_edge_cases(ctx):
+    F = rfb200.lu(np.zeros((0, 0), order="F"), ctx=ctx)
+    assert F.ipiv.size == 0 and F.info == 0
+    F = rfb200.lu(np.zeros((0, 5), order="F"), ctx=ctx)
+    assert F.ipiv.size == 0 and F.info == 0
+    F = rfb200.lu(np.zeros((130, 130), order="F"), check=False, ctx=ctx)
+    assert F.info == 1 and np.array_equal(F.ipiv, np.arange(1, 131))
+    eye = np.asfortranarray(np.eye(257))
+    F = rfb200.lu(eye, ctx=ctx)
+    assert np.array_equal(F.factors, eye) and np.array_equal(F.ipiv, np.arange(1, 258))
+    a = rand_matrix(np.random.default_rng(2), 300, 300, np.float64)
+    a[17, 0] = np.nan                                        # NaN is never chosen as pivot (src/lu.jl:301)
+    _, want_p, _ = O.lu_c(a.copy(order="F"))
+    F = rfb200.lu(a, check=False, ctx=ctx)
+    assert F.ipiv[0] == want_p[0] != 18
+
+
+@pytest.mark.parametrize("n", [4096])
+def test_baseline_config_4096(ctx, n):
+    """BASELINE config "4096x4096 Float64 LU with partial pivoting on 1 B200"."""
+    a0 = np.asfortranarray(np.random.default_rng(12).random((n, n)))
+    F = rfb200.lu(a0, ctx=ctx)
+    _, piv, info = lapack.dgetrf(a0)
+    assert F.info == info == 0
+    assert np.array_equal(F.ipiv, piv + 1)
+    res = O.residual_fro_rel(a0, F.factors, F.ipiv)
+    assert res <= 20 * n * np.finfo(np.float64).eps, res     # ||PA-LU||_F/||A||_F <= c n eps, c = 20
+    _, want_p, _ = O.lu_c(a0.copy(order="F"), threads=8)
+    assert np.array_equal(F.ipiv, want_p)
+
+
+def test_baseline_config_f32_8192_properties(ctx):
+    """BASELINE config "8192x8192 Float32": size-independent checks (oracle too slow at this size)."""
+    n = 8192
+    a0 = np.asfortranarray(np.random.default_rng(12).random((n, n), dtype=np.float32))
+    F = rfb200.lu(a0, ctx=ctx)
+    assert F.info == 0
+    assert sorted(O.perm_from_ipiv(F.ipiv, n).tolist()) == list(range(n))
+    assert np.all(np.abs(np.tril(F.factors, -1)) <= 1.0)     # partial pivoting => |L| <= 1
+    res = hutchinson_residual(a0, F.factors, F.ipiv)
+    assert res <= 20 * n * np.finfo(np.float32).eps, res
+
+
+def test_baseline_config_16384_properties(ctx):
+    """BASELINE config "16384x16384 Float64": |L| <= 1, valid permutation, residual probe."""
+    n = 16384
+    a0 = np.asfortranarray(np.random.default_rng(12).random((n, n)))
+    F = rfb200.lu(a0, ctx=ctx)
+    assert F.info == 0
+    assert sorted(O.perm_from_ipiv(F.ipiv, n).tolist()) == list(range(n))
+    assert np.all(np.abs(np.tril(F.factors, -1)) <= 1.0)
+    res = hutchinson_residual(a0, F.factors, F.ipiv)
+    assert res <= 20 * n * np.finfo(np.float64).eps, res
