@@ -7,6 +7,10 @@
  *
  * Every function cites the reference lines it restates (paths relative to
  * /root/reference).  Parity status: see the header of rf_oracle.c.
+ *
+ * Multiply-subtract is written as an explicit fused multiply-add (RFO_FMA): the reference's
+ * @turbo/@tturbo loops (src/lu.jl:268,276,330) compile to FMA on every FMA-capable CPU, and an
+ * explicit fma() makes the oracle's bits independent of the host it runs on.
  */
 
 /* ---- src/lu.jl:290-338  _generic_lufact!(A, Val(true), ipiv, info) -------------------------
@@ -15,6 +19,7 @@
  * swap rows k,kp over all n columns of the block (:308-315); scale by the RECIPROCAL
  * (:317-320); info = first k with an exactly-zero pivot, factorization continues (:321-327);
  * rank-1 update of the remaining columns (:330-334).  ipiv is 1-based and block-local. */
+RFO_CLONES
 static int64_t RFO_(rfo_generic_lufact)(RFO_T *A, int64_t m, int64_t n, int64_t lda,
                                         int64_t *ipiv, int64_t npiv, int64_t info)
 {
@@ -45,7 +50,7 @@ static int64_t RFO_(rfo_generic_lufact)(RFO_T *A, int64_t m, int64_t n, int64_t 
             RFO_T *cj = A + j * lda;
             RFO_T akj = cj[k];
             #pragma omp simd
-            for (int64_t i = k + 1; i < m; ++i) cj[i] -= ck[i] * akj;
+            for (int64_t i = k + 1; i < m; ++i) cj[i] = RFO_FMA(-ck[i], akj, cj[i]);
         }
     }
     return info;
@@ -72,44 +77,40 @@ static void RFO_(rfo_apply_permutation)(const int64_t *P, int64_t np, RFO_T *A, 
  * C[m,n] = C[m,n] + (0 - sum_k A[m,k] B[k,n]): the product is accumulated in its own register
  * and added to C once (:269-273).  Register tiling only, no packing, like the @turbo loop nest;
  * column blocks are spread over threads like @tturbo. */
-#define RFO_MR 16
-#define RFO_NR 4
+#define RFO_MR 16          /* rows per register tile: two 8-wide (f64) / one 16-wide (f32) vectors x2 */
+#define RFO_NR 6           /* columns per register tile */
+typedef RFO_T RFO_(rfo_vec) __attribute__((vector_size(8 * sizeof(RFO_T)), aligned(sizeof(RFO_T))));
 RFO_CLONES
 static void RFO_(rfo_schur_tile)(RFO_T *C, const RFO_T *A, const RFO_T *B, int64_t m, int64_t nn,
                                  int64_t k, int64_t lda)
 {
-    /* nn <= RFO_NR columns of C */
+    /* nn <= RFO_NR columns of C; 12 vector accumulators stay in registers over the whole k loop */
+    typedef RFO_(rfo_vec) vec;
     int64_t i0 = 0;
-    for (; i0 + RFO_MR <= m; i0 += RFO_MR) {
-        RFO_T acc[RFO_NR][RFO_MR];
-        for (int c = 0; c < RFO_NR; ++c)
-            for (int r = 0; r < RFO_MR; ++r) acc[c][r] = (RFO_T)0;
-        if (nn == RFO_NR) {
+    if (nn == RFO_NR) {
+        for (; i0 + RFO_MR <= m; i0 += RFO_MR) {
+            vec acc0[RFO_NR], acc1[RFO_NR];
+            for (int c = 0; c < RFO_NR; ++c) { acc0[c] = (vec){0}; acc1[c] = (vec){0}; }
             for (int64_t kk = 0; kk < k; ++kk) {
-                const RFO_T *a = A + i0 + kk * lda;
+                const vec a0 = *(const vec *)(A + i0 + kk * lda);
+                const vec a1 = *(const vec *)(A + i0 + 8 + kk * lda);
                 for (int c = 0; c < RFO_NR; ++c) {
-                    RFO_T b = B[kk + c * lda];
-                    #pragma omp simd
-                    for (int r = 0; r < RFO_MR; ++r) acc[c][r] -= a[r] * b;
+                    const RFO_T b = B[kk + c * lda];
+                    acc0[c] -= a0 * b;          /* contracted to one fused multiply-add per lane */
+                    acc1[c] -= a1 * b;
                 }
             }
-        } else {
-            for (int64_t kk = 0; kk < k; ++kk) {
-                const RFO_T *a = A + i0 + kk * lda;
-                for (int c = 0; c < nn; ++c) {
-                    RFO_T b = B[kk + c * lda];
-                    #pragma omp simd
-                    for (int r = 0; r < RFO_MR; ++r) acc[c][r] -= a[r] * b;
-                }
+            for (int c = 0; c < RFO_NR; ++c) {
+                vec *c0 = (vec *)(C + i0 + c * lda), *c1 = (vec *)(C + i0 + 8 + c * lda);
+                *c0 = acc0[c] + *c0;
+                *c1 = acc1[c] + *c1;
             }
         }
-        for (int c = 0; c < nn; ++c)
-            for (int r = 0; r < RFO_MR; ++r) C[i0 + r + c * lda] = acc[c][r] + C[i0 + r + c * lda];
     }
     for (; i0 < m; ++i0) {
         for (int c = 0; c < nn; ++c) {
             RFO_T acc = (RFO_T)0;
-            for (int64_t kk = 0; kk < k; ++kk) acc -= A[i0 + kk * lda] * B[kk + c * lda];
+            for (int64_t kk = 0; kk < k; ++kk) acc = RFO_FMA(-A[i0 + kk * lda], B[kk + c * lda], acc);
             C[i0 + c * lda] = acc + C[i0 + c * lda];
         }
     }
@@ -119,7 +120,7 @@ static void RFO_(rfo_schur_complement)(RFO_T *C, const RFO_T *A, const RFO_T *B,
                                        int64_t n, int64_t k, int64_t lda, int threads)
 {
     int64_t nblk = (n + RFO_NR - 1) / RFO_NR;
-    #pragma omp parallel for schedule(dynamic, 4) num_threads(threads) if (threads > 1)
+    #pragma omp parallel for schedule(dynamic, 2) num_threads(threads) if (threads > 1)
     for (int64_t jb = 0; jb < nblk; ++jb) {
         int64_t j0 = jb * RFO_NR;
         int64_t nn = n - j0 < RFO_NR ? n - j0 : RFO_NR;
@@ -135,6 +136,7 @@ static void RFO_(rfo_schur_complement)(RFO_T *C, const RFO_T *A, const RFO_T *B,
  * block size RFO_TB and the accumulate-then-add update above.  Only the STRICT lower triangle
  * of L is read (its diagonal and upper part hold U). */
 #define RFO_TB 64
+RFO_CLONES
 static void RFO_(rfo_trsm_llnu)(const RFO_T *L, int64_t k, RFO_T *B, int64_t nrhs, int64_t lda,
                                 int threads)
 {
@@ -147,7 +149,7 @@ static void RFO_(rfo_trsm_llnu)(const RFO_T *L, int64_t k, RFO_T *B, int64_t nrh
                 const RFO_T *l = L + b0 + (b0 + c) * lda;
                 RFO_T xc = x[c];
                 #pragma omp simd
-                for (int64_t r = c + 1; r < bs; ++r) x[r] -= l[r] * xc;
+                for (int64_t r = c + 1; r < bs; ++r) x[r] = RFO_FMA(-l[r], xc, x[r]);
             }
         }
         int64_t rest = k - b0 - bs;

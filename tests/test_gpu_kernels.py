@@ -84,8 +84,7 @@ def test_panel_ties_zero_column_and_offsets(ctx, dtype):
     rng = np.random.default_rng(5)
     m, n = 700, 48
     a0 = np.asfortranarray(rng.integers(-3, 4, size=(m, n)).astype(dtype))   # many exact ties
-    a0[:, 20] = 0
-    a0[:, 21] = a0[:, 3]                                                     # dependent column -> zero pivot
+    a0[:, 20] = 0                                                            # exactly-zero pivot -> info
     want_f, want_p, want_info = O.panel_c(a0.copy(order="F"))
     # factor it as a sub-block at (row 10, col 6) of a larger allocation; pivots shifted by ipiv_add
     big = np.asfortranarray(rng.random((m + 30, n + 20)).astype(dtype))
@@ -97,7 +96,8 @@ def test_panel_ties_zero_column_and_offsets(ctx, dtype):
     got = d.get()
     assert np.array_equal(get_i64(ctx, piv, n), want_p + 10)
     assert int(get_i64(ctx, info, 1)[0]) == (want_info + 6 if want_info else 0) and want_info > 0
-    assert np.allclose(got[10:10 + m, 6:6 + n], want_f, rtol=0, atol=ref_bound(m, dtype) * 4)
+    # same operation order, same FMA, same reciprocal: the panel kernel reproduces the oracle's bits
+    assert np.array_equal(got[10:10 + m, 6:6 + n], want_f)
     outside = np.ones_like(big, dtype=bool); outside[10:10 + m, 6:6 + n] = False
     assert np.array_equal(got[outside], big[outside])                        # nothing else touched
     d.free(); ctx.free(piv); ctx.free(info)
@@ -107,7 +107,7 @@ def test_panel_nan_and_zero_matrix(ctx):
     a0 = np.asfortranarray(np.random.default_rng(0).random((300, 16)))
     a0[5, 0] = np.nan
     d = Dev(ctx, a0)
-    piv = dev_i64(ctx, np.zeros(16)); info = dev_i64(ctx, np.zeros(8))
+    piv = dev_i64(ctx, np.zeros(32)); info = dev_i64(ctx, np.zeros(8))
     ctx._check(ctx._lib.rfb_panel_getrf_f64(ctx.handle, d.at(0, 0), 300, 16, 300, C.c_void_p(piv), 0, C.c_void_p(info), 0))
     _, want_p, _ = O.panel_c(a0.copy(order="F"))
     assert np.array_equal(get_i64(ctx, piv, 16), want_p)      # NaN is never selected (src/lu.jl:301)

@@ -14,13 +14,18 @@ def ref_bound(m, dtype):
     return 20.0 * m * float(np.finfo(dtype).eps)
 
 
-def assert_testlu(a0, factors, ipiv, info, info_expected):
-    """The reference's own acceptance test for a pivoted, serial factorization."""
+def assert_testlu(a0, factors, ipiv, info, info_expected, wide=False):
+    """The reference's own acceptance test for a pivoted, serial factorization.
+
+    `wide=True` is for shapes far outside the reference's sweep (its fat cases are only s x (s+2)):
+    the inf-norm sums over n columns, so E uses max(m, n); the CPU oracle itself needs that there
+    (1000 x 3000: 1.03e-11 against 20*m*eps = 4.4e-12).
+    """
     m, n = a0.shape
     assert info == info_expected                                   # runtests.jl:15
     if info != 0:
         return
-    e = ref_bound(m, a0.dtype)
+    e = ref_bound(max(m, n) if wide else m, a0.dtype)
     r = O.residual_inf(a0, factors, ipiv)
     assert r < e, f"||LU - A[p,:]||_inf = {r} >= {e}"              # runtests.jl:20
     if m == n and m > 0:                                           # runtests.jl:21-28
@@ -50,3 +55,25 @@ def hutchinson_residual(a0, factors, ipiv, nvec=8, seed=0):
     pax = np.asarray(a0, dtype=np.float64)[p, :] @ x
     num = np.linalg.norm(pax - lux) / np.sqrt(nvec)
     return float(num / np.linalg.norm(np.asarray(a0, dtype=np.float64)))
+
+
+def assert_pivots_match(a0, factors, ipiv, want_ipiv, strict):
+    """Pivot vectors must be identical.  With `strict=False` (Float32, where rounding noise of
+    different summation orders reaches the gap between the two largest candidates of a column --
+    SURVEY.md H4) a difference is accepted only if the FIRST differing step is a documented
+    near-tie: the row the oracle picked has |L| >= 1 - c*n*eps in our factorization, i.e. the two
+    candidates were equal to within the factorization's own error.  Everything after a legitimate
+    near-tie diverges by construction and is covered by the residual test."""
+    if np.array_equal(ipiv, want_ipiv):
+        return
+    assert not strict, f"pivot mismatch at step {int(np.argmax(np.asarray(ipiv) != np.asarray(want_ipiv)))}"
+    m, n = a0.shape
+    k = int(np.argmax(np.asarray(ipiv) != np.asarray(want_ipiv)))
+    perm_o = O.perm_from_ipiv(np.asarray(want_ipiv)[: k + 1], m)   # row the oracle moved to position k
+    perm_g = O.perm_from_ipiv(ipiv, m)
+    orig = perm_o[k]
+    pos = int(np.nonzero(perm_g == orig)[0][0])
+    assert pos > k, (k, pos)
+    ratio = abs(float(factors[pos, k]))
+    tol = 20 * max(m, n) * float(np.finfo(a0.dtype).eps)
+    assert ratio >= 1.0 - tol, f"pivot mismatch at step {k} is not a near-tie: |L[{pos},{k}]| = {ratio}"
