@@ -66,6 +66,8 @@ int rfb_create(rfb_ctx **out, int device);            /* one stream + workspace 
 int rfb_destroy(rfb_ctx *ctx);
 const char *rfb_last_error(rfb_ctx *ctx);             /* valid until the next call on ctx     */
 int rfb_device_info(rfb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *mem_bytes);
+/* options used by the kernel-level calls below (which take no rfb_opts); NULL restores defaults */
+int rfb_set_default_opts(rfb_ctx *ctx, const rfb_opts *opts);
 
 /* ---- whole path: twin of lu!(A, ipiv, Val(true), thread; check=false)  src/lu.jl:97-156 ----
  * Factors the m x n matrix in place (L strictly below the diagonal, U on/above: the layout of

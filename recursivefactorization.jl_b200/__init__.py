@@ -128,6 +128,14 @@ class Context:
     def sync(self):
         self._check(self._lib.rfb_sync(self._h))
 
+    def set_default_opts(self, **kw):
+        """Options for the kernel-level ABI calls (gemm_path, trsm_block, ...); no kwargs = defaults."""
+        if kw:
+            o = _make_opts(**kw)
+            self._check(self._lib.rfb_set_default_opts(self._h, C.byref(o)))
+        else:
+            self._check(self._lib.rfb_set_default_opts(self._h, None))
+
     def malloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self._lib.rfb_malloc(self._h, C.byref(p), nbytes))

@@ -110,12 +110,23 @@ struct PanelArgs {
     unsigned int epoch_base;
 };
 
+// Row-exchange list of one panel (consumed by the list-driven laswp, laswp.cu): which rows of the
+// panel changed place.  Slot k < n: pivot row k (dst = row0 + k).  Slot n + k: the row that the
+// k-th interchange displaced and that still sits there at the end.  Unused slots keep dst = -1
+// (the arrays are memset to 0xFF once per factorization).  Rows are absolute (root row 0).
+struct PanelPermOut {
+    int *dst;      // [2 n] slots of this panel, or nullptr
+    int *src;
+    int *width;    // width[0] = n
+    int row0;      // absolute row of the panel's first row
+};
+
 // Column step K of the panel.  K is a template parameter (and the steps are chained by template
 // recursion, not a loop) so that every index into the per-thread row `reg` is a compile-time
 // constant and the row provably stays in registers.
 template <typename T, int NB, int THREADS, int K>
 __device__ __forceinline__ void panel_steps(T (&reg)[NB], bool &alive, unsigned int &logpos, int &finalpos,
-                                            bool &bailed, PanelShared<T, NB, THREADS / 32> &sh,
+                                            int &dslot, bool &bailed, PanelShared<T, NB, THREADS / 32> &sh,
                                             const PanelArgs &pa) {
     if constexpr (K < NB) {
         constexpr int WARPS = THREADS / 32;
@@ -196,7 +207,7 @@ __device__ __forceinline__ void panel_steps(T (&reg)[NB], bool &alive, unsigned 
             alive = false;            // this row is pivot row K: frozen from now on
             finalpos = K;
         } else if (alive) {
-            if (logpos == (unsigned int)K) logpos = wb.lp;   // the swap K <-> kp, done on the index
+            if (logpos == (unsigned int)K) { logpos = wb.lp; dslot = K; }   // the swap K <-> kp, on the index
             T l = reg[K];
             if (pv != T(0)) l *= rcp_rn(pv);                 // reciprocal scaling (:317-320)
             reg[K] = l;
@@ -208,7 +219,7 @@ __device__ __forceinline__ void panel_steps(T (&reg)[NB], bool &alive, unsigned 
             pa.ipiv[K] = (long long)wb.lp + 1 + pa.ipiv_add;
             if (pv == T(0) && *pa.info == 0) *pa.info = pa.col_offset + K + 1;   // (:321-327)
         }
-        panel_steps<T, NB, THREADS, K + 1>(reg, alive, logpos, finalpos, bailed, sh, pa);
+        panel_steps<T, NB, THREADS, K + 1>(reg, alive, logpos, finalpos, dslot, bailed, sh, pa);
     }
 }
 
@@ -216,7 +227,7 @@ template <typename T, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ ipiv,
              long long ipiv_add, long long *__restrict__ info, long long col_offset,
-             RfbPanelXchg *__restrict__ x, unsigned int epoch_base) {
+             RfbPanelXchg *__restrict__ x, unsigned int epoch_base, PanelPermOut perm) {
     __shared__ PanelShared<T, NB, THREADS / 32> sh;
     PanelArgs pa;
     pa.n = n; pa.G = gridDim.x; pa.bid = blockIdx.x; pa.tid = threadIdx.x;
@@ -227,7 +238,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
 
     bool alive = row < m;
     unsigned int logpos = (unsigned int)row;
-    int finalpos = 0;
+    int finalpos = 0, dslot = 0;
     bool bailed = false;
 
     T reg[NB];
@@ -236,7 +247,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
     if (pa.tid < NB) { sh.u[0][pa.tid] = T(0); sh.u[1][pa.tid] = T(0); }
     __syncthreads();
 
-    panel_steps<T, NB, THREADS, 0>(reg, alive, logpos, finalpos, bailed, sh, pa);
+    panel_steps<T, NB, THREADS, 0>(reg, alive, logpos, finalpos, dslot, bailed, sh, pa);
 
     // -- single write-back, rows land at their final (swapped) position --------------------------
     if (row < m) {
@@ -244,18 +255,28 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
 #pragma unroll
         for (int j = 0; j < NB; ++j)
             if (j < n) A[dst + (long long)j * lda] = reg[j];
+        if (perm.dst != nullptr) {
+            if (!alive) {
+                perm.dst[finalpos] = perm.row0 + finalpos;
+                perm.src[finalpos] = perm.row0 + row;
+            } else if (logpos != (unsigned int)row) {
+                perm.dst[n + dslot] = perm.row0 + (int)logpos;
+                perm.src[n + dslot] = perm.row0 + row;
+            }
+        }
     }
+    if (perm.width != nullptr && pa.bid == 0 && pa.tid == 0) perm.width[0] = n;
 }
 
 template <typename T, int NB, int THREADS>
 int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
-                      int64_t *info, int64_t col_offset, int G) {
+                      int64_t *info, int64_t col_offset, int G, PanelPermOut perm) {
     auto kern = panel_kernel<T, NB, THREADS>;
     long long lda_ = lda, add_ = ipiv_add, off_ = col_offset;
     long long *ipiv_ = (long long *)ipiv, *info_ = (long long *)info;
     RfbPanelXchg *x = ctx->xchg;
     unsigned int epoch = ctx->panel_epoch;
-    void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch};
+    void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch, &perm};
     RfbLaunchScope scope(ctx, RFB_KC_PANEL, (double)m * n * n - (double)n * n * n / 3.0);
     if (G == 1) {
         RFB_CUDA(ctx, cudaLaunchKernel((const void *)kern, dim3(1), dim3(THREADS), args, 0, ctx->stream));
@@ -267,18 +288,25 @@ int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ip
 
 template <typename T, int THREADS>
 int launch_panel_threads(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
-                         int64_t *info, int64_t col_offset, int G) {
-    if (n <= 16) return launch_panel_inst<T, 16, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G);
-    if (n <= 32) return launch_panel_inst<T, 32, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G);
-    return launch_panel_inst<T, 64, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G);
+                         int64_t *info, int64_t col_offset, int G, PanelPermOut perm) {
+    if (n <= 16) return launch_panel_inst<T, 16, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G, perm);
+    if (n <= 32) return launch_panel_inst<T, 32, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G, perm);
+    return launch_panel_inst<T, 64, THREADS>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G, perm);
 }
 
 }  // namespace
 
 template <typename T>
 int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
-                     int64_t ipiv_add, int64_t *info_dev, int64_t col_offset) {
+                     int64_t ipiv_add, int64_t *info_dev, int64_t col_offset, int64_t perm_row0) {
     if (n <= 0 || m <= 0) return RFB_OK;
+    PanelPermOut perm{nullptr, nullptr, nullptr, 0};
+    if (perm_row0 >= 0 && ctx->perm_dst != nullptr) {     // whole-path driver: also emit the exchange list
+        perm.dst = ctx->perm_dst + 2 * perm_row0;
+        perm.src = ctx->perm_src + 2 * perm_row0;
+        perm.width = ctx->perm_width + perm_row0;
+        perm.row0 = (int)perm_row0;
+    }
     if (n > RFB_MAX_NB) return ctx->fail(RFB_ERR_UNSUPPORTED, "panel width %lld > %d", (long long)n, RFB_MAX_NB);
     if (m < n) return ctx->fail(RFB_ERR_ARG, "panel needs m >= n (got %lld x %lld)", (long long)m, (long long)n);
     // epoch hygiene: tags are 32 bit; restart the sequence (and wipe stale tags) long before wrap
@@ -290,9 +318,9 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
     int rc;
     const int64_t g128 = (m + 127) / 128, g256 = (m + 255) / 256;
     if (g128 <= max_ctas)
-        rc = launch_panel_threads<T, 128>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g128);
+        rc = launch_panel_threads<T, 128>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g128, perm);
     else if (g256 <= max_ctas)
-        rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256);
+        rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256, perm);
     else
         return ctx->fail(RFB_ERR_UNSUPPORTED, "panel with %lld rows exceeds one-row-per-thread capacity (%d)",
                          (long long)m, max_ctas * 256);
@@ -300,4 +328,4 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
     return rc;
 }
 
-template int rfb_launch_panel<RFB_PANEL_T>(rfb_ctx *, RFB_PANEL_T *, int64_t, int64_t, int64_t, int64_t *, int64_t, int64_t *, int64_t);
+template int rfb_launch_panel<RFB_PANEL_T>(rfb_ctx *, RFB_PANEL_T *, int64_t, int64_t, int64_t, int64_t *, int64_t, int64_t *, int64_t, int64_t);

@@ -24,8 +24,18 @@ namespace {
 
 struct LuPlan {
     int leaf;
+    bool lists;            // K1 emits row-exchange lists and K2 consumes them (default)
     const rfb_opts *opts;
 };
+
+// apply_permutation! (src/lu.jl:164-188) with pivots [k0, k0 + np) on the block whose first row is
+// absolute row k0
+template <typename T>
+int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv, int64_t k0, int64_t np,
+            const LuPlan &plan) {
+    if (plan.lists) return rfb_launch_laswp_lists<T>(ctx, A, ncols, lda, k0, k0 + np);
+    return rfb_launch_laswp<T>(ctx, A, ncols, lda, ipiv + k0, np, k0);
+}
 
 // reckernel! (src/lu.jl:189-263) on columns [c0, c0 + n) of the root matrix; the node's block is
 // rows [c0, m) (the diagonal block starts at row c0 == column c0).
@@ -35,15 +45,15 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
     T *A = root + c0 + c0 * lda;          // top-left of the node
     const int64_t mm = m - c0;            // rows of the node
     if (n <= plan.leaf)                   // :192-195 leaf -> K1
-        return rfb_launch_panel<T>(ctx, A, mm, n, lda, ipiv + c0, c0, info, c0);
+        return rfb_launch_panel<T>(ctx, A, mm, n, lda, ipiv + c0, c0, info, c0, plan.lists ? c0 : -1);
     const int64_t n1 = rfb_nsplit<T>(n), n2 = n - n1;                                   // :196-198
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n1, ipiv, info, plan));                    // :229
     T *AR = A + n1 * lda;
-    RFB_TRY(rfb_launch_laswp<T>(ctx, AR, n2, lda, ipiv + c0, n1, c0));                  // :233
+    RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));                          // :233
     RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan));               // :244
-    return rfb_launch_laswp<T>(ctx, A + n1, n1, lda, ipiv + c0 + n1, n2, c0 + n1);      // :246
+    return lu_swap<T>(ctx, A + n1, n1, lda, ipiv, c0 + n1, n2, plan);                   // :246
 }
 
 template <typename T>
@@ -57,10 +67,29 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t), ctx->stream));
     const int64_t mn = m < n ? m : n;
     if (mn == 0) return RFB_OK;
+    plan.lists = !(opts && opts->laswp_path == 1);
+    if (plan.lists) {
+        if ((size_t)mn > ctx->perm_cap) {
+            RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->perm_dst); cudaFree(ctx->perm_src); cudaFree(ctx->perm_width);
+            ctx->perm_dst = ctx->perm_src = ctx->perm_width = nullptr;
+            ctx->perm_cap = 0;
+            const size_t cap = (size_t)mn + 64;
+            if (cudaMalloc(&ctx->perm_dst, 2 * cap * sizeof(int)) != cudaSuccess ||
+                cudaMalloc(&ctx->perm_src, 2 * cap * sizeof(int)) != cudaSuccess ||
+                cudaMalloc(&ctx->perm_width, cap * sizeof(int)) != cudaSuccess) {
+                cudaGetLastError();
+                return ctx->fail(RFB_ERR_NOMEM, "cannot allocate the row-exchange lists");
+            }
+            ctx->perm_cap = cap;
+        }
+        RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_dst, 0xFF, 2 * (size_t)mn * sizeof(int), ctx->stream));
+        RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_width, 0, (size_t)mn * sizeof(int), ctx->stream));
+    }
     RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan));                   // :147
     if (m < n) {                                                                        // :148-154
         T *AR = dA + m * lda;
-        RFB_TRY(rfb_launch_laswp<T>(ctx, AR, n - m, lda, d_ipiv, mn, 0));
+        RFB_TRY(lu_swap<T>(ctx, AR, n - m, lda, d_ipiv, 0, mn, plan));
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
     return RFB_OK;
@@ -184,6 +213,9 @@ int rfb_destroy(rfb_ctx *ctx) {
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
     if (ctx->d_mat) cudaFree(ctx->d_mat);
+    if (ctx->perm_dst) cudaFree(ctx->perm_dst);
+    if (ctx->perm_src) cudaFree(ctx->perm_src);
+    if (ctx->perm_width) cudaFree(ctx->perm_width);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -201,6 +233,13 @@ int rfb_device_info(rfb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, s
     if (cc_major) *cc_major = ctx->cc_major;
     if (cc_minor) *cc_minor = ctx->cc_minor;
     if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+    return RFB_OK;
+}
+
+int rfb_set_default_opts(rfb_ctx *ctx, const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (opts) ctx->default_opts = *opts;
+    else ctx->default_opts = rfb_opts{};
     return RFB_OK;
 }
 
@@ -238,21 +277,21 @@ int rfb_laswp_f32(rfb_ctx *ctx, float *A, int64_t ncols, int64_t lda, const int6
 }
 int rfb_trsm_llnu_f64(rfb_ctx *ctx, const double *L, int64_t k, double *B, int64_t nrhs, int64_t lda) {
     RFB_CHECK_CTX(ctx);
-    return rfb_launch_trsm<double>(ctx, L, k, B, nrhs, lda, nullptr);
+    return rfb_launch_trsm<double>(ctx, L, k, B, nrhs, lda, &ctx->default_opts);
 }
 int rfb_trsm_llnu_f32(rfb_ctx *ctx, const float *L, int64_t k, float *B, int64_t nrhs, int64_t lda) {
     RFB_CHECK_CTX(ctx);
-    return rfb_launch_trsm<float>(ctx, L, k, B, nrhs, lda, nullptr);
+    return rfb_launch_trsm<float>(ctx, L, k, B, nrhs, lda, &ctx->default_opts);
 }
 int rfb_gemm_nn_sub_f64(rfb_ctx *ctx, double *C, const double *A, const double *B, int64_t m, int64_t n,
                         int64_t k, int64_t lda) {
     RFB_CHECK_CTX(ctx);
-    return rfb_launch_gemm<double>(ctx, C, A, B, m, n, k, lda, nullptr);
+    return rfb_launch_gemm<double>(ctx, C, A, B, m, n, k, lda, &ctx->default_opts);
 }
 int rfb_gemm_nn_sub_f32(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m, int64_t n, int64_t k,
                         int64_t lda) {
     RFB_CHECK_CTX(ctx);
-    return rfb_launch_gemm<float>(ctx, C, A, B, m, n, k, lda, nullptr);
+    return rfb_launch_gemm<float>(ctx, C, A, B, m, n, k, lda, &ctx->default_opts);
 }
 int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift) {
     RFB_CHECK_CTX(ctx);

@@ -37,6 +37,7 @@ struct rfb_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::string last_error;
+    rfb_opts default_opts = {};           // used by kernel-level ABI calls
 
     // workspaces
     RfbPanelXchg *xchg = nullptr;         // device
@@ -47,6 +48,9 @@ struct rfb_ctx {
     void *d_mat = nullptr;                // device matrix for HOST mem_space calls (grow-only)
     size_t d_mat_cap = 0;
     int64_t *h_pinned = nullptr;          // pinned scratch (info + small results)
+    // per-panel row-exchange lists written by K1 and consumed by the list-driven K2 (absolute rows)
+    int *perm_dst = nullptr, *perm_src = nullptr, *perm_width = nullptr;
+    size_t perm_cap = 0;                  // columns the three arrays are sized for
 
     // statistics
     int64_t launches = 0;
@@ -116,7 +120,11 @@ struct RfbLaunchScope {
 // ---- kernel launchers (each enqueues on ctx->stream, returns RFB_* status) --------------------
 template <typename T>
 int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
-                     int64_t ipiv_add, int64_t *info_dev, int64_t col_offset);
+                     int64_t ipiv_add, int64_t *info_dev, int64_t col_offset, int64_t perm_row0 = -1);
+// list-driven row interchange: applies the exchange lists of the panels covering pivots [k0, k1)
+// to the (rows >= k0) x ncols block whose first row is absolute row k0
+template <typename T>
+int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1);
 template <typename T>
 int rfb_launch_laswp(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
                      int64_t npiv, int64_t ipiv_sub);

@@ -22,13 +22,24 @@ trsm_diag_kernel(const T *__restrict__ L, int kb, T *__restrict__ B, long long n
     const int tid = threadIdx.x;
     const long long col0 = (long long)blockIdx.x * COLS;
 
-    for (int idx = tid; idx < TB * TB; idx += COLS) {
-        const int r = idx % TB, c = idx / TB;
-        sL[c * TB + r] = (r < kb && c < kb && r > c) ? L[r + (long long)c * lda] : T(0);
-    }
-    for (int idx = tid; idx < TB * COLS; idx += COLS) {
-        const int r = idx % TB, cc = idx / TB;
-        sB[cc * (TB + 1) + r] = (r < kb && col0 + cc < nrhs) ? B[r + (col0 + cc) * lda] : T(0);
+    static_assert(COLS == TB, "tile loads below assume one thread per tile row");
+    // tile loads: thread `tid` owns row `tid`; 16 independent global loads are in flight before the
+    // first shared store (a plain load->store loop serialises on the possible aliasing)
+#pragma unroll
+    for (int c0 = 0; c0 < TB; c0 += 16) {
+        T tl[16], tb_[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = c0 + u;
+            tl[u] = (tid < kb && c < kb && tid > c) ? L[tid + (long long)c * lda] : T(0);
+            tb_[u] = (tid < kb && col0 + c < nrhs) ? B[tid + (col0 + c) * lda] : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = c0 + u;
+            sL[c * TB + tid] = tl[u];
+            sB[c * (TB + 1) + tid] = tb_[u];
+        }
     }
     __syncthreads();
 
@@ -45,15 +56,20 @@ trsm_diag_kernel(const T *__restrict__ L, int kb, T *__restrict__ B, long long n
     for (int r = 0; r < TB; ++r) sB[tid * (TB + 1) + r] = x[r];
     __syncthreads();
 
-    for (int idx = tid; idx < TB * COLS; idx += COLS) {
-        const int r = idx % TB, cc = idx / TB;
-        if (r < kb && col0 + cc < nrhs) B[r + (col0 + cc) * lda] = sB[cc * (TB + 1) + r];
+#pragma unroll
+    for (int c0 = 0; c0 < TB; c0 += 16) {
+        T tb_[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tb_[u] = sB[(c0 + u) * (TB + 1) + tid];
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            if (tid < kb && col0 + c0 + u < nrhs) B[tid + (col0 + c0 + u) * lda] = tb_[u];
     }
 }
 
 template <typename T, int TB>
 int launch_diag(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
-    constexpr int COLS = 64;
+    constexpr int COLS = TB;
     constexpr size_t smem = sizeof(T) * (TB * TB + COLS * (TB + 1));
     auto kern = trsm_diag_kernel<T, TB, COLS>;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));

@@ -1,0 +1,29 @@
+"""Small targets for ncu captures: `python scripts/ncu_target.py lu N` or `gemm M N K path`."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rfb200  # noqa: E402
+
+ctx = rfb200.Context(0)
+what = sys.argv[1]
+if what == "lu":
+    n = int(sys.argv[2])
+    a = np.asfortranarray(np.random.default_rng(12).random((n, n)))
+    d = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
+    d.upload(a)
+    d.lu()
+    ctx.sync()
+elif what == "gemm":
+    m, n, k, path = (int(x) for x in sys.argv[2:6])
+    lda = m + k
+    big = ctx.malloc(lda * (n + k) * 8)
+    ctx.memset(big, 0, lda * (n + k) * 8)
+    at = lambda r, c: C.c_void_p(big + (r + c * lda) * 8)
+    ctx.set_default_opts(gemm_path=path)
+    for _ in range(2):
+        ctx._check(ctx._lib.rfb_gemm_nn_sub_f64(ctx.handle, at(k, k), at(k, 0), at(0, k), m, n, k, lda))
+    ctx.sync()
