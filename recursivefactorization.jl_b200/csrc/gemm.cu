@@ -117,23 +117,27 @@ gemm_f64_generic_kernel(double *__restrict__ C, const double *__restrict__ A, co
     }
     cp_async_wait<0>();
 
-    // epilogue: C = C - acc  (the "+ (0 - sum)" of src/lu.jl:269-273)
+    // epilogue: C = C - acc  (the "+ (0 - sum)" of src/lu.jl:269-273); the 8 loads of a fragment row
+    // are issued before the first store so that they overlap
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = m0 + wm + i * 8 + g;
         if (r >= M) continue;
+        double cv[4][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = n0 + wn + j * 8 + 2 * q;
-            if (c < N) {
-                double *p = C + r + (long long)c * lda;
-                *p = *p - acc[i][j][0];
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = n0 + wn + j * 8 + 2 * q + e;
+                cv[j][e] = c < N ? C[r + (long long)c * lda] : 0.0;
             }
-            if (c + 1 < N) {
-                double *p = C + r + (long long)(c + 1) * lda;
-                *p = *p - acc[i][j][1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = n0 + wn + j * 8 + 2 * q + e;
+                if (c < N) C[r + (long long)c * lda] = cv[j][e] - acc[i][j][e];
             }
-        }
     }
 }
 

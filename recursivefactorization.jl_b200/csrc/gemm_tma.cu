@@ -175,19 +175,52 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
-    // epilogue: C = C - acc (src/lu.jl:269-273), rows/cols through the fragment maps
+    // epilogue: C = C - acc (src/lu.jl:269-273).  The accumulators are first parked in the (now idle)
+    // pipeline buffers as a dense column-major 128 x 128 tile -- undoing the fragment permutation --
+    // so that the read-modify-write of C runs as fully coalesced 16-byte accesses with 8 independent
+    // loads in flight per thread (a direct per-fragment RMW serialises 64 load->store round trips).
+    __syncthreads();                                   // every warp is done reading the last stage
+    double *sC = reinterpret_cast<double *>(base);     // [n 0..127][m 0..127]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int r = m0 + wm + (i >> 1) * kABoxRows + a_row_in_box(g, i & 1);
-        if (r >= M) continue;
+        const int r = wm + (i >> 1) * kABoxRows + a_row_in_box(g, i & 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = n0 + wn + j * 8 + b_col_in_tile(2 * q + e);
-                if (c < N) {
-                    double *p = C + r + (long long)c * lda;
-                    *p = *p - acc[i][j][e];
+                const int c = wn + j * 8 + b_col_in_tile(2 * q + e);
+                sC[c * TBM + r] = acc[i][j][e];
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int rp = (tid & 63) * 2;                 // row pair inside the tile
+        const int cb = tid >> 6;                       // 0..3
+        const int gr = m0 + rp;
+#pragma unroll
+        for (int it0 = 0; it0 < TBN / 4; it0 += 8) {
+            double2 cv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = cb + 4 * (it0 + u);
+                const int gc = n0 + c;
+                cv[u] = make_double2(0.0, 0.0);
+                if (gc < N) {
+                    const double *p = C + gr + (long long)gc * lda;
+                    if (gr + 1 < M) cv[u] = *reinterpret_cast<const double2 *>(p);
+                    else if (gr < M) cv[u].x = *p;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = cb + 4 * (it0 + u);
+                const int gc = n0 + c;
+                if (gc < N) {
+                    const double2 a2 = *reinterpret_cast<const double2 *>(sC + c * TBM + rp);
+                    double *p = C + gr + (long long)gc * lda;
+                    if (gr + 1 < M) *reinterpret_cast<double2 *>(p) = make_double2(cv[u].x - a2.x, cv[u].y - a2.y);
+                    else if (gr < M) *p = cv[u].x - a2.x;
                 }
             }
         }
@@ -217,7 +250,9 @@ int rfb_launch_gemm_f64_tma(rfb_ctx *ctx, double *C, const double *A, const doub
                             int64_t k, int64_t lda, bool *handled) {
     *handled = false;
     if (!ctx->encode_tiled) return RFB_OK;
-    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 1)) return RFB_OK;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+        (reinterpret_cast<uintptr_t>(C) & 15) || (lda & 1))
+        return RFB_OK;
     if (lda * 8 >= (int64_t(1) << 40)) return RFB_OK;
     CUtensorMap mapA, mapB;
     if (!make_map(ctx, &mapA, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda * 8, kABoxRows, TBK)) return RFB_OK;

@@ -19,6 +19,7 @@
 //     make the slots reusable without a second sync); every CTA then reduces the G headers
 //     redundantly and reads the winner's row.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "rfb_internal.h"
 
@@ -100,16 +101,6 @@ struct PanelShared {
     ReduceBuf<WARPS> glb[2];
 };
 
-struct PanelArgs {
-    int n, G, bid, tid, lane, warp;
-    long long *ipiv;
-    long long ipiv_add;
-    long long *info;
-    long long col_offset;
-    RfbPanelXchg *x;
-    unsigned int epoch_base;
-};
-
 // Row-exchange list of one panel (consumed by the list-driven laswp, laswp.cu): which rows of the
 // panel changed place.  Slot k < n: pivot row k (dst = row0 + k).  Slot n + k: the row that the
 // k-th interchange displaced and that still sits there at the end.  Unused slots keep dst = -1
@@ -121,51 +112,74 @@ struct PanelPermOut {
     int row0;      // absolute row of the panel's first row
 };
 
-// Column step K of the panel.  K is a template parameter (and the steps are chained by template
-// recursion, not a loop) so that every index into the per-thread row `reg` is a compile-time
-// constant and the row provably stays in registers.
-template <typename T, int NB, int THREADS, int K>
-__device__ __forceinline__ void panel_steps(T (&reg)[NB], bool &alive, unsigned int &logpos, int &finalpos,
-                                            int &dslot, bool &bailed, PanelShared<T, NB, THREADS / 32> &sh,
-                                            const PanelArgs &pa) {
-    if constexpr (K < NB) {
-        constexpr int WARPS = THREADS / 32;
-        if (K >= pa.n) return;
-        constexpr int par = K & 1;
-        const unsigned int epoch = pa.epoch_base + (unsigned int)K;
-        const int tid = pa.tid, bid = pa.bid, n = pa.n;
-        RfbPanelXchg *x = pa.x;
+// The column loop is a REAL loop (not unrolled over k): the per-thread row is kept as a sliding
+// register window -- reg[j] always holds column k + j, and the rank-1 update writes its result one
+// register to the left (reg[j-1] = reg[j] - l * u[j]) -- so every step executes the same few
+// hundred instructions out of the instruction cache.  (A version unrolled over k, 51k SASS
+// instructions for NB = 64, spent ~3 us per column in instruction-fetch stalls.)  Finished values
+// leave the window through a shared-memory tile fin[column][thread] and are written to global
+// memory once, at the row's final position.
+template <typename T, int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ ipiv,
+             long long ipiv_add, long long *__restrict__ info, long long col_offset,
+             RfbPanelXchg *__restrict__ x, unsigned int epoch_base, PanelPermOut perm) {
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char panel_smem[];
+    T *fin = reinterpret_cast<T *>(panel_smem);                 // [NB][THREADS]
+    __shared__ PanelShared<T, NB, WARPS> sh;
+
+    const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row = bid * THREADS + tid;
+
+    bool alive = row < m;
+    unsigned int logpos = (unsigned int)row;
+    int finalpos = 0, dslot = 0;
+    bool bailed = false;
+
+    T reg[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) reg[j] = (alive && j < n) ? A[row + (long long)j * lda] : T(0);
+    if (tid < NB) { sh.u[0][tid] = T(0); sh.u[1][tid] = T(0); }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        const int par = k & 1;
+        const int rem = n - k;                                   // live width of the window
+        const unsigned int epoch = epoch_base + (unsigned int)k;
 
         // -- local candidate (src/lu.jl:296-305) ------------------------------------------------
-        const T av = fabs(reg[K]);
+        const T av = fabs(reg[0]);
         Cand c;
         c.key = (alive && av > T(0)) ? to_bits(av) : 0ull;
         c.lp = alive ? logpos : kNone;
         c.src = (unsigned int)bid;
-        const Cand cb = block_best<WARPS>(c, sh.loc[par], pa.warp, pa.lane);
+        const Cand cb = block_best<WARPS>(c, sh.loc[par], warp, lane);
         const bool cta_winner = alive && logpos == cb.lp;
 
         Cand wb;
-        if (pa.G == 1) {
+        if (G == 1) {
             wb = cb;
             if (cta_winner) {
 #pragma unroll
-                for (int j = K; j < NB; ++j) sh.u[par][j] = reg[j];
+                for (int j = 0; j < NB; ++j) sh.u[par][j] = reg[j];
             }
             __syncthreads();
         } else {
-            // -- publish this CTA's candidate and its row -------------------------------------
+            // -- publish this CTA's candidate (header first, then its row window) ---------------
             if (cta_winner) {
-#pragma unroll
-                for (int j = K; j < NB; ++j)
-                    if (j < n) st_xchg(&x->row[par][bid][j], to_bits(reg[j]), (unsigned long long)epoch);
                 st_xchg(&x->header[par][bid], cb.key, ((unsigned long long)epoch << 32) | cb.lp);
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if (j < rem) st_xchg(&x->row[par][bid][j], to_bits(reg[j]), (unsigned long long)epoch);
             } else if (cb.lp == kNone && tid == 0) {
                 st_xchg(&x->header[par][bid], 0ull, ((unsigned long long)epoch << 32) | kNone);
             }
-            // -- gather all G headers, reduce redundantly in every CTA ------------------------
+            // -- gather all G headers, reduce redundantly in every CTA --------------------------
             Cand g{0ull, kNone, 0u};
-            for (int cta = tid; cta < pa.G; cta += THREADS) {
+            for (int cta = tid; cta < G; cta += THREADS) {
                 ulonglong2 h;
                 unsigned int spins = 0;
                 while (true) {
@@ -181,80 +195,58 @@ __device__ __forceinline__ void panel_steps(T (&reg)[NB], bool &alive, unsigned 
                 const unsigned int hl = (unsigned int)h.y;
                 if (better(h.x, hl, g.key, g.lp)) { g.key = h.x; g.lp = hl; g.src = (unsigned int)cta; }
             }
-            wb = block_best<WARPS>(g, sh.glb[par], pa.warp, pa.lane);
-            // -- fetch the winning row --------------------------------------------------------
-            if (tid >= K && tid < n) {
-                ulonglong2 d;
-                unsigned int spins = 0;
-                while (true) {
-                    d = ld_xchg(&x->row[par][wb.src][tid]);
-                    if ((unsigned int)d.y == epoch) break;
-                    if (bailed) break;
-                    if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
-                        atomicExch(&x->error_flag, 1u);
-                        bailed = true;
-                        break;
+            wb = block_best<WARPS>(g, sh.glb[par], warp, lane);
+            // -- fetch the winning row window -----------------------------------------------------
+            if (tid < NB) {
+                T val = T(0);
+                if (tid < rem) {
+                    ulonglong2 d;
+                    unsigned int spins = 0;
+                    while (true) {
+                        d = ld_xchg(&x->row[par][wb.src][tid]);
+                        if ((unsigned int)d.y == epoch) break;
+                        if (bailed) break;
+                        if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
+                            atomicExch(&x->error_flag, 1u);
+                            bailed = true;
+                            break;
+                        }
                     }
+                    val = from_bits<T>(d.x);
                 }
-                sh.u[par][tid] = from_bits<T>(d.x);
+                sh.u[par][tid] = val;
             }
             __syncthreads();
         }
 
         // -- eliminate (src/lu.jl:307-334) ------------------------------------------------------
-        const T pv = sh.u[par][K];
+        const T pv = sh.u[par][0];
         if (alive && logpos == wb.lp) {
-            alive = false;            // this row is pivot row K: frozen from now on
-            finalpos = K;
+            alive = false;            // this row is pivot row k: frozen; its window is row k of U
+            finalpos = k;
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (j < rem) fin[(k + j) * THREADS + tid] = reg[j];
         } else if (alive) {
-            if (logpos == (unsigned int)K) { logpos = wb.lp; dslot = K; }   // the swap K <-> kp, on the index
-            T l = reg[K];
+            if (logpos == (unsigned int)k) { logpos = wb.lp; dslot = k; }   // the swap k <-> kp, on the index
+            T l = reg[0];
             if (pv != T(0)) l *= rcp_rn(pv);                 // reciprocal scaling (:317-320)
-            reg[K] = l;
+            fin[k * THREADS + tid] = l;
             const T nl = -l;
 #pragma unroll
-            for (int j = K + 1; j < NB; ++j) reg[j] = fma(nl, sh.u[par][j], reg[j]);
+            for (int j = 1; j < NB; ++j) reg[j - 1] = fma(nl, sh.u[par][j], reg[j]);   // slide the window
+            reg[NB - 1] = T(0);
         }
         if (bid == 0 && tid == 0) {
-            pa.ipiv[K] = (long long)wb.lp + 1 + pa.ipiv_add;
-            if (pv == T(0) && *pa.info == 0) *pa.info = pa.col_offset + K + 1;   // (:321-327)
+            ipiv[k] = (long long)wb.lp + 1 + ipiv_add;
+            if (pv == T(0) && *info == 0) *info = col_offset + k + 1;   // (:321-327)
         }
-        panel_steps<T, NB, THREADS, K + 1>(reg, alive, logpos, finalpos, dslot, bailed, sh, pa);
     }
-}
-
-template <typename T, int NB, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ ipiv,
-             long long ipiv_add, long long *__restrict__ info, long long col_offset,
-             RfbPanelXchg *__restrict__ x, unsigned int epoch_base, PanelPermOut perm) {
-    __shared__ PanelShared<T, NB, THREADS / 32> sh;
-    PanelArgs pa;
-    pa.n = n; pa.G = gridDim.x; pa.bid = blockIdx.x; pa.tid = threadIdx.x;
-    pa.lane = threadIdx.x & 31; pa.warp = threadIdx.x >> 5;
-    pa.ipiv = ipiv; pa.ipiv_add = ipiv_add; pa.info = info; pa.col_offset = col_offset;
-    pa.x = x; pa.epoch_base = epoch_base;
-    const int row = pa.bid * THREADS + pa.tid;
-
-    bool alive = row < m;
-    unsigned int logpos = (unsigned int)row;
-    int finalpos = 0, dslot = 0;
-    bool bailed = false;
-
-    T reg[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) reg[j] = (alive && j < n) ? A[row + (long long)j * lda] : T(0);
-    if (pa.tid < NB) { sh.u[0][pa.tid] = T(0); sh.u[1][pa.tid] = T(0); }
-    __syncthreads();
-
-    panel_steps<T, NB, THREADS, 0>(reg, alive, logpos, finalpos, dslot, bailed, sh, pa);
 
     // -- single write-back, rows land at their final (swapped) position --------------------------
     if (row < m) {
         const long long dst = alive ? (long long)logpos : (long long)finalpos;
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-            if (j < n) A[dst + (long long)j * lda] = reg[j];
+        for (int j = 0; j < n; ++j) A[dst + (long long)j * lda] = fin[j * THREADS + tid];
         if (perm.dst != nullptr) {
             if (!alive) {
                 perm.dst[finalpos] = perm.row0 + finalpos;
@@ -265,7 +257,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
             }
         }
     }
-    if (perm.width != nullptr && pa.bid == 0 && pa.tid == 0) perm.width[0] = n;
+    if (perm.width != nullptr && bid == 0 && tid == 0) perm.width[0] = n;
 }
 
 template <typename T, int NB, int THREADS>
@@ -277,11 +269,13 @@ int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ip
     RfbPanelXchg *x = ctx->xchg;
     unsigned int epoch = ctx->panel_epoch;
     void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch, &perm};
+    constexpr size_t smem = sizeof(T) * NB * THREADS;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
     RfbLaunchScope scope(ctx, RFB_KC_PANEL, (double)m * n * n - (double)n * n * n / 3.0);
     if (G == 1) {
-        RFB_CUDA(ctx, cudaLaunchKernel((const void *)kern, dim3(1), dim3(THREADS), args, 0, ctx->stream));
+        RFB_CUDA(ctx, cudaLaunchKernel((const void *)kern, dim3(1), dim3(THREADS), args, smem, ctx->stream));
     } else {
-        RFB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(THREADS), args, 0, ctx->stream));
+        RFB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(THREADS), args, smem, ctx->stream));
     }
     return RFB_OK;
 }
@@ -317,7 +311,8 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
     const int max_ctas = ctx->sm_count < RFB_MAX_PANEL_CTAS ? ctx->sm_count : RFB_MAX_PANEL_CTAS;
     int rc;
     const int64_t g128 = (m + 127) / 128, g256 = (m + 255) / 256;
-    if (g128 <= max_ctas)
+    static const int force_threads = getenv("RFB_PANEL_THREADS") ? atoi(getenv("RFB_PANEL_THREADS")) : 0;   // tuning aid
+    if (g128 <= max_ctas && force_threads != 256)
         rc = launch_panel_threads<T, 128>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g128, perm);
     else if (g256 <= max_ctas)
         rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256, perm);

@@ -11,66 +11,49 @@
 namespace {
 
 // Diagonal block solve.  One thread owns one right-hand-side column and keeps its TB values in
-// registers; L is staged in shared memory and read as warp-wide broadcasts; the B tile goes
-// through a padded shared tile so that global traffic is coalesced down the columns.
+// registers for the whole solve; L is staged once in shared memory and read as warp-wide
+// broadcasts.  Memory is touched in exactly two round trips: all TB loads of the L tile are in
+// flight together, then all TB loads of the thread's own column (each thread reads and writes whole
+// 32-byte sectors of its column, and the 128-byte lines are shared through L1, so going straight
+// from global memory to registers costs no extra DRAM traffic).
 template <typename T, int TB, int COLS>
 __global__ void __launch_bounds__(COLS)
 trsm_diag_kernel(const T *__restrict__ L, int kb, T *__restrict__ B, long long nrhs, long long lda) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sL = reinterpret_cast<T *>(smem_raw);          // [TB cols][TB rows], zero outside strict lower
-    T *sB = sL + TB * TB;                             // [COLS][TB + 1]
+    static_assert(COLS == TB, "the L tile load assumes one thread per tile row");
     const int tid = threadIdx.x;
-    const long long col0 = (long long)blockIdx.x * COLS;
-
-    static_assert(COLS == TB, "tile loads below assume one thread per tile row");
-    // tile loads: thread `tid` owns row `tid`; 16 independent global loads are in flight before the
-    // first shared store (a plain load->store loop serialises on the possible aliasing)
+    const long long col = (long long)blockIdx.x * COLS + tid;
+    const bool active = col < nrhs;
+    {
+        T tl[TB];
 #pragma unroll
-    for (int c0 = 0; c0 < TB; c0 += 16) {
-        T tl[16], tb_[16];
+        for (int c = 0; c < TB; ++c) tl[c] = (tid < kb && c < kb && tid > c) ? L[tid + (long long)c * lda] : T(0);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int c = c0 + u;
-            tl[u] = (tid < kb && c < kb && tid > c) ? L[tid + (long long)c * lda] : T(0);
-            tb_[u] = (tid < kb && col0 + c < nrhs) ? B[tid + (col0 + c) * lda] : T(0);
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int c = c0 + u;
-            sL[c * TB + tid] = tl[u];
-            sB[c * (TB + 1) + tid] = tb_[u];
-        }
+        for (int c = 0; c < TB; ++c) sL[c * TB + tid] = tl[c];
     }
-    __syncthreads();
-
+    T *xcol = B + (active ? col : 0) * lda;
     T x[TB];
 #pragma unroll
-    for (int r = 0; r < TB; ++r) x[r] = sB[tid * (TB + 1) + r];
+    for (int r = 0; r < TB; ++r) x[r] = (active && r < kb) ? xcol[r] : T(0);
+    __syncthreads();
 #pragma unroll
     for (int c = 0; c < TB - 1; ++c) {
         const T nxc = -x[c];
 #pragma unroll
         for (int r = c + 1; r < TB; ++r) x[r] = fma(sL[c * TB + r], nxc, x[r]);
     }
+    if (active) {
 #pragma unroll
-    for (int r = 0; r < TB; ++r) sB[tid * (TB + 1) + r] = x[r];
-    __syncthreads();
-
-#pragma unroll
-    for (int c0 = 0; c0 < TB; c0 += 16) {
-        T tb_[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) tb_[u] = sB[(c0 + u) * (TB + 1) + tid];
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-            if (tid < kb && col0 + c0 + u < nrhs) B[tid + (col0 + c0 + u) * lda] = tb_[u];
+        for (int r = 0; r < TB; ++r)
+            if (r < kb) xcol[r] = x[r];
     }
 }
 
 template <typename T, int TB>
 int launch_diag(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
     constexpr int COLS = TB;
-    constexpr size_t smem = sizeof(T) * (TB * TB + COLS * (TB + 1));
+    constexpr size_t smem = sizeof(T) * (TB * TB);
     auto kern = trsm_diag_kernel<T, TB, COLS>;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
     RfbLaunchScope scope(ctx, RFB_KC_TRSM, (double)kb * (double)kb * (double)nrhs);

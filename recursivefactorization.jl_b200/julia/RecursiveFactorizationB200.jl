@@ -1,0 +1,150 @@
+# RecursiveFactorizationB200.jl -- Julia host layer over librfb200.so (C ABI: include/rfb200.h).
+#
+# STATUS: shipped UN-EXECUTED.  No Julia runtime exists in the build image or on the GPU box, so
+# this file has never been run; the executable twin used by the tests and benchmarks is the Python
+# package next to it (same C calls through ctypes).  It is written against the reference's public
+# surface (RecursiveFactorization.jl 0.2.30):
+#
+#   lu(A, pivot = Val(true), thread = Val(false); kwargs...)            src/lu.jl:19-21
+#   lu!(A, pivot = Val(true), thread = Val(false); check, kwargs...)    src/lu.jl:67-83
+#   lu!(A, ipiv, pivot, thread; check, blocksize, threshold)            src/lu.jl:97-130
+#
+# and returns the same LinearAlgebra.LU{T,Matrix{T},Vector{BlasInt}} (src/lu.jl:129): the caller's
+# matrix mutated in place, the caller's pivot vector, info.  `thread`, `blocksize` and `threshold`
+# are accepted and ignored (they tune the CPU kernels); `leaf_width` is the GPU analogue.
+# Unsupported inputs (pivot = Val(false)/NoPivot(), complex or generic eltypes, non-strided
+# arrays) throw -- there is deliberately no CPU fallback.
+module RecursiveFactorizationB200
+
+using LinearAlgebra
+using LinearAlgebra: BlasInt, LU, checknonsingular
+
+const librfb200 = get(ENV, "RFB200_LIB", joinpath(@__DIR__, "..", "librfb200.so"))
+
+# mirror of `struct rfb_opts` (16 x Int32)
+struct RfbOpts
+    mem_space::Int32
+    leaf_width::Int32
+    f32_mode::Int32
+    trsm_block::Int32
+    gemm_path::Int32
+    laswp_path::Int32
+    reserved::NTuple{10, Int32}
+end
+RfbOpts(; mem_space = 0, leaf_width = 0, f32_mode = 0, trsm_block = 0, gemm_path = 0, laswp_path = 0) =
+    RfbOpts(mem_space, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, ntuple(_ -> Int32(0), 10))
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:rfb_create, librfb200), Cint, (Ptr{Ptr{Cvoid}}, Cint), ref, device)
+        ctx = new(ref[])
+        rc == 0 || (msg = last_error(ctx); destroy!(ctx); error("rfb_create failed ($rc): $msg"))
+        finalizer(destroy!, ctx)
+        return ctx
+    end
+end
+last_error(ctx::Context) =
+    ctx.handle == C_NULL ? "null context" :
+    unsafe_string(ccall((:rfb_last_error, librfb200), Cstring, (Ptr{Cvoid},), ctx.handle))
+function destroy!(ctx::Context)
+    ctx.handle == C_NULL && return
+    ccall((:rfb_destroy, librfb200), Cint, (Ptr{Cvoid},), ctx.handle)
+    ctx.handle = C_NULL
+    return
+end
+
+# one context per task (a context is not thread-safe, see rfb200.h)
+default_context() = get!(() -> Context(parse(Int, get(ENV, "LOCAL_RANK", "0"))), task_local_storage(), :rfb200_ctx)::Context
+
+# pivot normalisation, same accepted spellings as src/lu.jl:10-17
+normalize_pivot(::Val{true}) = true
+normalize_pivot(::Val{false}) = false
+normalize_pivot(::LinearAlgebra.RowMaximum) = true
+normalize_pivot(::LinearAlgebra.NoPivot) = false
+
+_wants_check(check::Bool) = check
+_wants_check(::Val{true}) = true
+_wants_check(::Val{false}) = false
+
+for (T, sym) in ((Float64, :rfb_lu_f64), (Float32, :rfb_lu_f32))
+    @eval function _rfb_lu!(ctx::Context, A::StridedMatrix{$T}, ipiv::Vector{BlasInt}, opts::RfbOpts)
+        m, n = size(A)
+        stride(A, 1) == 1 || throw(ArgumentError("rfb200 needs unit row stride (column-major storage)"))
+        info = Ref{Int64}(0)
+        o = Ref(opts)
+        rc = GC.@preserve A ipiv ccall(($(QuoteNode(sym)), librfb200), Cint,
+            (Ptr{Cvoid}, Ptr{$T}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{RfbOpts}),
+            ctx.handle, pointer(A), m, n, max(1, stride(A, 2)), pointer(ipiv), info, o)
+        rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+        return info[]
+    end
+end
+
+function lu!(A::StridedMatrix{T}, ipiv::AbstractVector{<:Integer}, pivot = Val(true), thread = Val(false);
+        check::Union{Bool, Val{true}, Val{false}} = Val(true),
+        blocksize::Integer = 0, threshold::Integer = 0,          # accepted, ignored (CPU knobs)
+        leaf_width::Integer = 0, ctx::Context = default_context()) where {T <: Union{Float64, Float32}}
+    normalize_pivot(pivot) || throw(ArgumentError("pivot = Val(false)/NoPivot() is outside the B200 hot path"))
+    BlasInt === Int64 || error("rfb200 writes Int64 pivots; this Julia has BlasInt = $BlasInt")
+    length(ipiv) == min(size(A)...) || throw(DimensionMismatch("ipiv must have length min(m, n)"))
+    piv = ipiv isa Vector{BlasInt} ? ipiv : Vector{BlasInt}(undef, length(ipiv))
+    info = _rfb_lu!(ctx, A, piv, RfbOpts(leaf_width = leaf_width))
+    piv === ipiv || copyto!(ipiv, piv)
+    _wants_check(check) && checknonsingular(info)                # SingularException, src/lu.jl:128
+    return LU(A, ipiv, BlasInt(info))                            # src/lu.jl:129
+end
+
+function lu!(A::StridedMatrix{T}, pivot = Val(true), thread = Val(false); kwargs...) where {T <: Union{Float64, Float32}}
+    ipiv = Vector{BlasInt}(undef, min(size(A)...))               # init_pivot, src/lu.jl:40
+    return lu!(A, ipiv, pivot, thread; kwargs...)
+end
+
+lu(A::AbstractMatrix, pivot = Val(true), thread = Val(false); kwargs...) =
+    lu!(copy(A), pivot, thread; kwargs...)                       # src/lu.jl:19-21
+
+# Adjoint / Transpose wrappers, same contract as src/lu.jl:85-87
+for (f, W) in ((:adjoint, :Adjoint), (:transpose, :Transpose)), g in (:lu, :lu!)
+    @eval $g(A::$W, args...; kwargs...) = $f($g(parent(A), args...; kwargs...))
+end
+
+# everything else is not on the GPU path: fail loudly instead of silently running on the CPU
+lu!(A::AbstractMatrix, args...; kwargs...) =
+    throw(ArgumentError("rfb200 supports strided Float64/Float32 matrices only, got $(typeof(A))"))
+
+# ---------------------------------------------------------------------------------------------
+# Julia-driven recursion over the kernel-level ABI: the restatement of reckernel! (src/lu.jl:189-263)
+# a Julia maintainer would own if the recursion is to stay in Julia (north_star).  `dA`, `dipiv`,
+# `dinfo` are device pointers (rfb_malloc / rfb_h2d); pivots are produced in global coordinates by
+# passing the node's row offset as `ipiv_add`, so no P2 .+= n1 pass is needed.
+# ---------------------------------------------------------------------------------------------
+nsplit(::Type{T}, n) where {T} = (k = max(2, 128 ÷ sizeof(T)); n >= k ? ((n + k ÷ 2) ÷ k) * (k ÷ 2) : n ÷ 2)
+
+function reckernel_device!(ctx::Context, dA::Ptr{Float64}, m, lda, c0, n, dipiv::Ptr{Int64}, dinfo::Ptr{Int64}; leaf = 64)
+    at(r, c) = dA + 8 * (r + c * lda)
+    A = at(c0, c0); mm = m - c0
+    chk(rc) = rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+    if n <= leaf
+        chk(ccall((:rfb_panel_getrf_f64, librfb200), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64),
+            ctx.handle, A, mm, n, lda, dipiv + 8 * c0, c0, dinfo, c0))
+        return
+    end
+    n1 = nsplit(Float64, n); n2 = n - n1
+    reckernel_device!(ctx, dA, m, lda, c0, n1, dipiv, dinfo; leaf)
+    AR = at(c0, c0 + n1)
+    chk(ccall((:rfb_laswp_f64, librfb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64, Int64),
+        ctx.handle, AR, n2, lda, dipiv + 8 * c0, n1, c0))
+    chk(ccall((:rfb_trsm_llnu_f64, librfb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64),
+        ctx.handle, A, n1, AR, n2, lda))
+    chk(ccall((:rfb_gemm_nn_sub_f64, librfb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Int64),
+        ctx.handle, at(c0 + n1, c0 + n1), at(c0 + n1, c0), AR, mm - n1, n2, n1, lda))
+    reckernel_device!(ctx, dA, m, lda, c0 + n1, n2, dipiv, dinfo; leaf)
+    chk(ccall((:rfb_laswp_f64, librfb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64, Int64),
+        ctx.handle, at(c0 + n1, c0), n1, lda, dipiv + 8 * (c0 + n1), n2, c0 + n1))
+    return
+end
+
+end # module

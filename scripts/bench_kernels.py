@@ -37,8 +37,10 @@ for m in (64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768):
     t = timed(run) - timed(copy_only)
     res[m] = round(t * 1e3 / 64, 3)
     ctx.free(d); ctx.free(d2)
-out["panel_us_per_column_n64"] = res
+out["panel_us_per_column_n64_T%s" % os.environ.get("RFB_PANEL_THREADS", "auto")] = res
 print("panel us/col", res, flush=True)
+if os.environ.get("PANEL_ONLY"):
+    sys.exit(0)
 
 # ---- gemm -----------------------------------------------------------------------------------------
 res = {}
