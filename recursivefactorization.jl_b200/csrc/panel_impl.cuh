@@ -28,12 +28,16 @@ namespace {
 constexpr unsigned int kNone = 0xFFFFFFFFu;
 constexpr unsigned int kSpinLimit = 1u << 22;
 
+// Exchange words live in L2 only: st.cg writes through to L2, ld.cv re-fetches from L2 on every
+// poll.  Measured on B200 (scripts/xchg_bench2.cu): cg/cv + one 128-byte line per header + a
+// warp-wide row store give 0.51-0.66 us per two-phase exchange for 1..128 CTAs, against 1.1-3.6 us
+// for volatile accesses, packed headers and a single thread storing the 64 row words.
 __device__ __forceinline__ void st_xchg(ulonglong2 *p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ ulonglong2 ld_xchg(const ulonglong2 *p) {
     ulonglong2 r;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    asm volatile("ld.global.cv.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
@@ -60,15 +64,22 @@ struct Cand {
 __device__ __forceinline__ bool better(unsigned long long k1, unsigned int lp1, unsigned long long k2, unsigned int lp2) {
     return k1 > k2 || (k1 == k2 && lp1 < lp2);
 }
+// Warp argmax with three redux.sync instead of a 5-round shuffle butterfly: max of the key's high
+// word, max of the low word among the lanes that hold that high word, then the lowest logical row
+// among the lanes that hold the full key.
 __device__ __forceinline__ Cand warp_best(Cand c) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        unsigned long long ok = __shfl_xor_sync(0xffffffffu, c.key, off);
-        unsigned int olp = __shfl_xor_sync(0xffffffffu, c.lp, off);
-        unsigned int os = __shfl_xor_sync(0xffffffffu, c.src, off);
-        if (better(ok, olp, c.key, c.lp)) { c.key = ok; c.lp = olp; c.src = os; }
-    }
-    return c;
+    const unsigned int hi = (unsigned int)(c.key >> 32), lo = (unsigned int)c.key;
+    const unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const bool in1 = hi == mhi;
+    const unsigned int mlo = __reduce_max_sync(0xffffffffu, in1 ? lo : 0u);
+    const bool in2 = in1 && lo == mlo;
+    const unsigned int mlp = __reduce_min_sync(0xffffffffu, in2 ? c.lp : kNone);
+    const unsigned int who = __ballot_sync(0xffffffffu, in2 && c.lp == mlp);
+    Cand r;
+    r.key = ((unsigned long long)mhi << 32) | mlo;
+    r.lp = mlp;
+    r.src = __shfl_sync(0xffffffffu, c.src, who ? (__ffs(who) - 1) : 0);
+    return r;
 }
 
 template <int WARPS>
@@ -97,6 +108,7 @@ __device__ __forceinline__ Cand block_best(Cand c, ReduceBuf<WARPS> &buf, int wa
 template <typename T, int NB, int WARPS>
 struct PanelShared {
     T u[2][NB];
+    T pub[NB];          // staging of the CTA winner's row window for the warp-wide publish
     ReduceBuf<WARPS> loc[2];
     ReduceBuf<WARPS> glb[2];
 };
@@ -170,12 +182,17 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         } else {
             // -- publish this CTA's candidate (header first, then its row window) ---------------
             if (cta_winner) {
-                st_xchg(&x->header[par][bid], cb.key, ((unsigned long long)epoch << 32) | cb.lp);
+                st_xchg(&x->header[par][bid].h, cb.key, ((unsigned long long)epoch << 32) | cb.lp);
 #pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if (j < rem) st_xchg(&x->row[par][bid][j], to_bits(reg[j]), (unsigned long long)epoch);
+                for (int j = 0; j < NB; ++j) sh.pub[j] = reg[j];
             } else if (cb.lp == kNone && tid == 0) {
-                st_xchg(&x->header[par][bid], 0ull, ((unsigned long long)epoch << 32) | kNone);
+                st_xchg(&x->header[par][bid].h, 0ull, ((unsigned long long)epoch << 32) | kNone);
+            }
+            if (__ballot_sync(0xffffffffu, cta_winner)) {       // the winner's warp stores the row together
+                __syncwarp();
+#pragma unroll
+                for (int j = lane; j < NB; j += 32)
+                    if (j < rem) st_xchg(&x->row[par][bid][j], to_bits(sh.pub[j]), (unsigned long long)epoch);
             }
             // -- gather all G headers, reduce redundantly in every CTA --------------------------
             Cand g{0ull, kNone, 0u};
@@ -183,7 +200,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                 ulonglong2 h;
                 unsigned int spins = 0;
                 while (true) {
-                    h = ld_xchg(&x->header[par][cta]);
+                    h = ld_xchg(&x->header[par][cta].h);
                     if ((unsigned int)(h.y >> 32) == epoch) break;
                     if (bailed) break;
                     if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {

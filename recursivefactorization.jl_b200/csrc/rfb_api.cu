@@ -6,6 +6,7 @@
 //     `P2 .+= n1` (:256-260) and `info += n1` (:248-255) fix-ups have nothing left to do;
 //   * recursion stops at `leaf_width` columns (default 64) instead of blocksize 8/16 (:101): one
 //     K1 launch factors the whole leaf panel.
+#include <algorithm>
 #include <cstdarg>
 
 #include "rfb_internal.h"
@@ -26,7 +27,23 @@ struct LuPlan {
     int leaf;
     bool lists;            // K1 emits row-exchange lists and K2 consumes them (default)
     const rfb_opts *opts;
+    // pipelined upload (host mode): column chunk i is resident once up_events[i] has fired
+    std::vector<cudaEvent_t> *up_events = nullptr;
+    int64_t up_chunk = 0;  // columns per chunk
+    int up_waited = -1;    // last chunk the compute stream already waits for
 };
+
+// The compute stream is about to touch columns [0, ncols): make it wait for their upload.
+static int need_cols(rfb_ctx *ctx, LuPlan &plan, int64_t ncols) {
+    if (!plan.up_events || ncols <= 0) return RFB_OK;
+    int last = (int)((ncols - 1) / plan.up_chunk);
+    if (last >= (int)plan.up_events->size()) last = (int)plan.up_events->size() - 1;
+    while (plan.up_waited < last) {
+        plan.up_waited++;
+        RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, (*plan.up_events)[plan.up_waited], 0));
+    }
+    return RFB_OK;
+}
 
 // apply_permutation! (src/lu.jl:164-188) with pivots [k0, k0 + np) on the block whose first row is
 // absolute row k0
@@ -41,14 +58,17 @@ int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv,
 // rows [c0, m) (the diagonal block starts at row c0 == column c0).
 template <typename T>
 int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
-           const LuPlan &plan) {
+           LuPlan &plan) {
     T *A = root + c0 + c0 * lda;          // top-left of the node
     const int64_t mm = m - c0;            // rows of the node
-    if (n <= plan.leaf)                   // :192-195 leaf -> K1
+    if (n <= plan.leaf) {                 // :192-195 leaf -> K1
+        RFB_TRY(need_cols(ctx, plan, c0 + n));
         return rfb_launch_panel<T>(ctx, A, mm, n, lda, ipiv + c0, c0, info, c0, plan.lists ? c0 : -1);
+    }
     const int64_t n1 = rfb_nsplit<T>(n), n2 = n - n1;                                   // :196-198
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n1, ipiv, info, plan));                    // :229
     T *AR = A + n1 * lda;
+    RFB_TRY(need_cols(ctx, plan, c0 + n));
     RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));                          // :233
     RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
@@ -58,9 +78,11 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
 
 template <typename T>
 int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d_ipiv, int64_t *d_info,
-              const rfb_opts *opts) {
+              const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, int64_t up_chunk = 0) {
     LuPlan plan;
     plan.opts = opts;
+    plan.up_events = up_events;
+    plan.up_chunk = up_chunk;
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
         return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
@@ -89,6 +111,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan));                   // :147
     if (m < n) {                                                                        // :148-154
         T *AR = dA + m * lda;
+        RFB_TRY(need_cols(ctx, plan, n));
         RFB_TRY(lu_swap<T>(ctx, AR, n - m, lda, d_ipiv, 0, mn, plan));
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
@@ -139,9 +162,27 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
         ctx->d_ipiv_cap = (size_t)mn;
     }
     T *dA = reinterpret_cast<T *>(ctx->d_mat);
-    RFB_CUDA(ctx, cudaMemcpy2DAsync(dA, sizeof(T) * ldd, A, sizeof(T) * lda, sizeof(T) * m, n,
-                                    cudaMemcpyHostToDevice, ctx->stream));
-    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, ctx->d_ipiv, ctx->d_info, opts));
+    // Pipelined upload: column chunks go up on the copy stream in order; the factorization is
+    // left-looking, so it starts as soon as the first chunk is resident and the rest of the upload
+    // hides behind the work on the left columns.
+    const int64_t chunk_cols = std::max<int64_t>(64, (int64_t)((size_t(64) << 20) / (sizeof(T) * (size_t)ldd)));
+    const int nchunks = (int)((n + chunk_cols - 1) / chunk_cols);
+    while ((int)ctx->up_events.size() < nchunks) {
+        cudaEvent_t e;
+        RFB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->up_events.push_back(e);
+    }
+    RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));          // the staging buffer is free again
+    RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t j0 = (int64_t)c * chunk_cols, nc = std::min<int64_t>(chunk_cols, n - j0);
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(dA + j0 * ldd, sizeof(T) * ldd, A + j0 * lda, sizeof(T) * lda, sizeof(T) * m,
+                                        nc, cudaMemcpyHostToDevice, ctx->copy_stream));
+        RFB_CUDA(ctx, cudaEventRecord(ctx->up_events[c], ctx->copy_stream));
+    }
+    std::vector<cudaEvent_t> evs(ctx->up_events.begin(), ctx->up_events.begin() + nchunks);
+    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols));
+    RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
     RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * lda, dA, sizeof(T) * ldd, sizeof(T) * m, n,
                                     cudaMemcpyDeviceToHost, ctx->stream));
     RFB_CUDA(ctx, cudaMemcpyAsync(ipiv, ctx->d_ipiv, sizeof(int64_t) * mn, cudaMemcpyDeviceToHost, ctx->stream));
@@ -187,6 +228,7 @@ int rfb_create(rfb_ctx **out, int device) {
     RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
     RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_stop));
+    RFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
     RFB_CUDA(ctx, cudaMalloc(&ctx->xchg, sizeof(RfbPanelXchg)));
     RFB_CUDA(ctx, cudaMemset(ctx->xchg, 0, sizeof(RfbPanelXchg)));
     RFB_CUDA(ctx, cudaMalloc(&ctx->d_info, 64));
@@ -209,6 +251,7 @@ int rfb_destroy(rfb_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream);
     }
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->up_events) cudaEventDestroy(e);
     if (ctx->xchg) cudaFree(ctx->xchg);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
@@ -219,6 +262,7 @@ int rfb_destroy(rfb_ctx *ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;

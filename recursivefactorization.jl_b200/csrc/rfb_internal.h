@@ -17,9 +17,14 @@
 constexpr int RFB_MAX_PANEL_CTAS = 296;   // 148 SMs x 2
 constexpr int RFB_MAX_NB = 64;            // widest panel one launch factors
 
+struct alignas(128) RfbPanelHeader {   // one 128-byte line per CTA: 148 pollers do not pile up on one L2 line
+    ulonglong2 h;
+    ulonglong2 pad[7];
+};
+
 struct RfbPanelXchg {
-    // header[parity][cta] = { |candidate| bits , (epoch << 32) | logical row }
-    ulonglong2 header[2][RFB_MAX_PANEL_CTAS];
+    // header[parity][cta].h = { |candidate| bits , (epoch << 32) | logical row }
+    RfbPanelHeader header[2][RFB_MAX_PANEL_CTAS];
     // row[parity][cta][j] = { candidate row value in column j (raw bits) , epoch }
     ulonglong2 row[2][RFB_MAX_PANEL_CTAS][RFB_MAX_NB];
     unsigned int error_flag;              // set by a kernel whose poll loop gave up
@@ -35,7 +40,7 @@ struct rfb_ctx {
     size_t mem_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_sync = nullptr;
     std::string last_error;
     rfb_opts default_opts = {};           // used by kernel-level ABI calls
 
@@ -51,6 +56,8 @@ struct rfb_ctx {
     // per-panel row-exchange lists written by K1 and consumed by the list-driven K2 (absolute rows)
     int *perm_dst = nullptr, *perm_src = nullptr, *perm_width = nullptr;
     size_t perm_cap = 0;                  // columns the three arrays are sized for
+
+    std::vector<cudaEvent_t> up_events;   // upload-chunk events of host-mode calls (reused)
 
     // statistics
     int64_t launches = 0;
