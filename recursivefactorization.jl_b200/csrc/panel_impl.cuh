@@ -28,17 +28,23 @@ namespace {
 constexpr unsigned int kNone = 0xFFFFFFFFu;
 constexpr unsigned int kSpinLimit = 1u << 22;
 
-// Exchange words live in L2 only: st.cg writes through to L2, ld.cv re-fetches from L2 on every
-// poll.  Measured on B200 (scripts/xchg_bench2.cu): cg/cv + one 128-byte line per header + a
-// warp-wide row store give 0.51-0.66 us per two-phase exchange for 1..128 CTAs, against 1.1-3.6 us
-// for volatile accesses, packed headers and a single thread storing the 64 row words.
-__device__ __forceinline__ void st_xchg(ulonglong2 *p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+// Exchange accesses are *strong* relaxed gpu-scope operations on 8-byte self-tagged words
+// ({epoch : 32 | payload : 32}); two words travel in one 16-byte vector access but each half is
+// validated on its own, so nothing depends on 16-byte single-copy atomicity.  (Weak st.cg / ld.cv
+// look faster in a microbenchmark but are not a legal communication pair: with them this kernel
+// read stale rows.)  Measured on B200 (scripts/xchg_bench*.cu): one 128-byte line per header and
+// a warp-wide row store take the two-phase exchange from 1.1-3.6 us to under 1 us for 2..128 CTAs.
+__device__ __forceinline__ void st_tagged(ulonglong2 *p, unsigned int epoch, unsigned int lo, unsigned int hi) {
+    const unsigned long long a = ((unsigned long long)epoch << 32) | lo, b = ((unsigned long long)epoch << 32) | hi;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ ulonglong2 ld_xchg(const ulonglong2 *p) {
-    ulonglong2 r;
-    asm volatile("ld.global.cv.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
-    return r;
+// returns true when both halves carry `epoch`; lo/hi are the payloads
+__device__ __forceinline__ bool ld_tagged(const ulonglong2 *p, unsigned int epoch, unsigned int &lo, unsigned int &hi) {
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    lo = (unsigned int)a;
+    hi = (unsigned int)b;
+    return (unsigned int)(a >> 32) == epoch && (unsigned int)(b >> 32) == epoch;
 }
 __device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
     unsigned int r;
@@ -182,26 +188,32 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         } else {
             // -- publish this CTA's candidate (header first, then its row window) ---------------
             if (cta_winner) {
-                st_xchg(&x->header[par][bid].h, cb.key, ((unsigned long long)epoch << 32) | cb.lp);
+                st_tagged(&x->header[par][bid].h[0], epoch, (unsigned int)cb.key, (unsigned int)(cb.key >> 32));
+                st_tagged(&x->header[par][bid].h[1], epoch, cb.lp, 0u);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) sh.pub[j] = reg[j];
             } else if (cb.lp == kNone && tid == 0) {
-                st_xchg(&x->header[par][bid].h, 0ull, ((unsigned long long)epoch << 32) | kNone);
+                st_tagged(&x->header[par][bid].h[0], epoch, 0u, 0u);
+                st_tagged(&x->header[par][bid].h[1], epoch, kNone, 0u);
             }
             if (__ballot_sync(0xffffffffu, cta_winner)) {       // the winner's warp stores the row together
                 __syncwarp();
 #pragma unroll
                 for (int j = lane; j < NB; j += 32)
-                    if (j < rem) st_xchg(&x->row[par][bid][j], to_bits(sh.pub[j]), (unsigned long long)epoch);
+                    if (j < rem) {
+                        const unsigned long long bits = to_bits(sh.pub[j]);
+                        st_tagged(&x->row[par][bid][j], epoch, (unsigned int)bits, (unsigned int)(bits >> 32));
+                    }
             }
             // -- gather all G headers, reduce redundantly in every CTA --------------------------
             Cand g{0ull, kNone, 0u};
             for (int cta = tid; cta < G; cta += THREADS) {
-                ulonglong2 h;
+                unsigned int klo, khi, hl, spare;
                 unsigned int spins = 0;
                 while (true) {
-                    h = ld_xchg(&x->header[par][cta].h);
-                    if ((unsigned int)(h.y >> 32) == epoch) break;
+                    const bool ok0 = ld_tagged(&x->header[par][cta].h[0], epoch, klo, khi);
+                    const bool ok1 = ld_tagged(&x->header[par][cta].h[1], epoch, hl, spare);
+                    if (ok0 && ok1) break;
                     if (bailed) break;
                     if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
                         atomicExch(&x->error_flag, 1u);
@@ -209,19 +221,18 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                         break;
                     }
                 }
-                const unsigned int hl = (unsigned int)h.y;
-                if (better(h.x, hl, g.key, g.lp)) { g.key = h.x; g.lp = hl; g.src = (unsigned int)cta; }
+                const unsigned long long hk = ((unsigned long long)khi << 32) | klo;
+                if (better(hk, hl, g.key, g.lp)) { g.key = hk; g.lp = hl; g.src = (unsigned int)cta; }
             }
             wb = block_best<WARPS>(g, sh.glb[par], warp, lane);
             // -- fetch the winning row window -----------------------------------------------------
             if (tid < NB) {
                 T val = T(0);
                 if (tid < rem) {
-                    ulonglong2 d;
+                    unsigned int vlo, vhi;
                     unsigned int spins = 0;
                     while (true) {
-                        d = ld_xchg(&x->row[par][wb.src][tid]);
-                        if ((unsigned int)d.y == epoch) break;
+                        if (ld_tagged(&x->row[par][wb.src][tid], epoch, vlo, vhi)) break;
                         if (bailed) break;
                         if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
                             atomicExch(&x->error_flag, 1u);
@@ -229,7 +240,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                             break;
                         }
                     }
-                    val = from_bits<T>(d.x);
+                    val = from_bits<T>(((unsigned long long)vhi << 32) | vlo);
                 }
                 sh.u[par][tid] = val;
             }

@@ -191,8 +191,10 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
                                   cudaMemcpyDeviceToHost, ctx->stream));
     RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *info = ctx->h_pinned[0];
-    if ((unsigned int)ctx->h_pinned[1] != 0)
+    if ((unsigned int)ctx->h_pinned[1] != 0) {
+        cudaMemset(&ctx->xchg->error_flag, 0, sizeof(unsigned int));   // report once, keep the context usable
         return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+    }
     return RFB_OK;
 }
 
@@ -398,7 +400,10 @@ int rfb_sync(rfb_ctx *ctx) {
     RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned int flag = 0;
     RFB_CUDA(ctx, cudaMemcpy(&flag, &ctx->xchg->error_flag, sizeof(flag), cudaMemcpyDeviceToHost));
-    if (flag) return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+    if (flag) {
+        cudaMemset(&ctx->xchg->error_flag, 0, sizeof(unsigned int));       // report once, keep the context usable
+        return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+    }
     return RFB_OK;
 }
 

@@ -11,21 +11,22 @@
 #include "../../include/rfb200.h"
 
 // ---------------------------------------------------------------------------------------------
-// Panel exchange workspace (K1).  One slot per CTA and step parity.  Every 16-byte word carries
-// its own epoch tag, so a reader never needs a fence: it polls until the tag matches.
+// Panel exchange workspace (K1).  One slot per CTA and step parity.  Every 8-byte word is
+// { epoch tag : 32 | payload : 32 } (the NCCL "LL" idea), so a reader never needs a fence and never
+// depends on 16-byte atomicity: it polls until the tags of all words it needs match the step.
 // ---------------------------------------------------------------------------------------------
 constexpr int RFB_MAX_PANEL_CTAS = 296;   // 148 SMs x 2
 constexpr int RFB_MAX_NB = 64;            // widest panel one launch factors
 
 struct alignas(128) RfbPanelHeader {   // one 128-byte line per CTA: 148 pollers do not pile up on one L2 line
-    ulonglong2 h;
-    ulonglong2 pad[7];
+    ulonglong2 h[2];                   // four tagged words: key lo, key hi, logical row, spare
+    ulonglong2 pad[6];
 };
 
 struct RfbPanelXchg {
-    // header[parity][cta].h = { |candidate| bits , (epoch << 32) | logical row }
+    // header[parity][cta].h = tagged { |candidate| bits lo, hi } and { logical row, 0 }
     RfbPanelHeader header[2][RFB_MAX_PANEL_CTAS];
-    // row[parity][cta][j] = { candidate row value in column j (raw bits) , epoch }
+    // row[parity][cta][j] = tagged { lo, hi } halves of the candidate row's value in window column j
     ulonglong2 row[2][RFB_MAX_PANEL_CTAS][RFB_MAX_NB];
     unsigned int error_flag;              // set by a kernel whose poll loop gave up
     unsigned int pad[3];
