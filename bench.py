@@ -79,7 +79,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -202,13 +202,14 @@ def run_ours(args, rank, world, local_rank):
     dmma_peak = ctx.dmma_peak_tflops(20000)
 
     # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)     # started before the warm-up: nvidia-smi needs ~0.5 s to come up
+    sampler.start()
+    time.sleep(0.5)
     for _ in range(args.warmup):
         work.copy_from(pristine)
         work.lu()
     ctx.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_count()
     times = []
     for _ in range(args.steps):
