@@ -110,6 +110,32 @@ int rfb_gemm_nn_sub_f32(rfb_ctx *ctx, float *C, const float *A, const float *B, 
                         int64_t n, int64_t k, int64_t lda);
 int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);
 
+/* ---- building blocks of the multi-GPU driver (1-D block-cyclic columns) ----
+ * The distributed recursion runs on the host (recursivefactorization.jl_b200/dist_lu.py, one process
+ * per GPU); each rank holds a full-size column-major buffer in which its own block columns and the
+ * received L panels are valid, and calls:
+ * rfb_lu_range: reckernel! (src/lu.jl:189-263) on columns [c0, c0+n) of the root matrix (rows
+ *   c0..m), pivots and info in GLOBAL coordinates, exchange lists recorded for rfb_laswp_range.
+ * rfb_laswp_range: apply_permutation! (src/lu.jl:164-188) with pivots [k0, k1) to columns
+ *   [col0, col0+ncols) (rows >= k0) of the root matrix, list-driven when the lists of those
+ *   pivots are present (factored or received on this rank), ipiv-driven otherwise.
+ * rfb_perm_buffers: caller-owned device arrays for the exchange lists (dst, src: 2*cap int32,
+ *   width: cap int32) so that they can be broadcast with the panel; resets them.
+ */
+int rfb_lu_range_f64(rfb_ctx *ctx, double *A_root, int64_t m, int64_t lda, int64_t c0, int64_t n,
+                     int64_t *ipiv_dev, int64_t *info_dev, const rfb_opts *opts);
+int rfb_lu_range_f32(rfb_ctx *ctx, float *A_root, int64_t m, int64_t lda, int64_t c0, int64_t n,
+                     int64_t *ipiv_dev, int64_t *info_dev, const rfb_opts *opts);
+int rfb_laswp_range_f64(rfb_ctx *ctx, double *A_root, int64_t lda, int64_t col0, int64_t ncols,
+                        int64_t k0, int64_t k1, const int64_t *ipiv_dev, int use_lists);
+int rfb_laswp_range_f32(rfb_ctx *ctx, float *A_root, int64_t lda, int64_t col0, int64_t ncols,
+                        int64_t k0, int64_t k1, const int64_t *ipiv_dev, int use_lists);
+int rfb_perm_buffers(rfb_ctx *ctx, int32_t *dst_dev, int32_t *src_dev, int32_t *width_dev, int64_t cap);
+int rfb_copy2d(rfb_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch,
+               size_t width_bytes, size_t height);                               /* async d2d      */
+/* enqueue on a caller-provided CUDA stream (e.g. torch's current stream); NULL restores the own one */
+int rfb_set_stream(rfb_ctx *ctx, void *cuda_stream);
+
 /* ---- memory / stream plumbing ------------------------------------------------------------- */
 int rfb_malloc(rfb_ctx *ctx, void **dev_ptr, size_t bytes);
 int rfb_free(rfb_ctx *ctx, void *dev_ptr);

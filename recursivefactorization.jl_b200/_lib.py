@@ -55,6 +55,13 @@ SIGNATURES = {
     "rfb_gemm_nn_sub_f64": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64]),
     "rfb_gemm_nn_sub_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64]),
     "rfb_ipiv_shift": (_int, [_p, _p, _i64, _i64]),
+    "rfb_lu_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
+    "rfb_lu_range_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
+    "rfb_laswp_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),
+    "rfb_laswp_range_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),
+    "rfb_perm_buffers": (_int, [_p, _p, _p, _p, _i64]),
+    "rfb_copy2d": (_int, [_p, _p, C.c_size_t, _p, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "rfb_set_stream": (_int, [_p, _p]),
     "rfb_malloc": (_int, [_p, C.POINTER(_p), C.c_size_t]),
     "rfb_free": (_int, [_p, _p]),
     "rfb_host_alloc": (_int, [_p, C.POINTER(_p), C.c_size_t]),

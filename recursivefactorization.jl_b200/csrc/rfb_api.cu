@@ -92,6 +92,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     plan.lists = !(opts && opts->laswp_path == 1);
     if (plan.lists) {
         if ((size_t)mn > ctx->perm_cap) {
+            if (ctx->perm_external) return ctx->fail(RFB_ERR_ARG, "caller-provided exchange-list buffers are too small");
             RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ctx->perm_dst); cudaFree(ctx->perm_src); cudaFree(ctx->perm_width);
             ctx->perm_dst = ctx->perm_src = ctx->perm_width = nullptr;
@@ -116,6 +117,40 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
     return RFB_OK;
+}
+
+// reckernel! on a column range of the root (multi-GPU building block); needs the exchange-list arrays
+template <typename T>
+int lu_range(rfb_ctx *ctx, T *A_root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
+             const rfb_opts *opts) {
+    if (!A_root || !ipiv || !info) return ctx->fail(RFB_ERR_ARG, "rfb_lu_range: null pointer");
+    if (c0 < 0 || n < 0 || c0 + n > m || lda < m) return ctx->fail(RFB_ERR_ARG, "rfb_lu_range: bad range/lda");
+    if (n == 0) return RFB_OK;
+    RFB_CUDA(ctx, cudaSetDevice(ctx->device));
+    LuPlan plan;
+    plan.opts = opts;
+    plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
+    if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
+        return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
+    plan.lists = !(opts && opts->laswp_path == 1);
+    if (plan.lists && (ctx->perm_dst == nullptr || (size_t)(c0 + n) > ctx->perm_cap))
+        return ctx->fail(RFB_ERR_ARG, "rfb_lu_range: exchange-list buffers missing or too small (rfb_perm_buffers)");
+    return lu_rec<T>(ctx, A_root, m, lda, c0, n, ipiv, info, plan);
+}
+
+template <typename T>
+int laswp_range(rfb_ctx *ctx, T *A_root, int64_t lda, int64_t col0, int64_t ncols, int64_t k0, int64_t k1,
+                const int64_t *ipiv, int use_lists) {
+    if (!A_root) return ctx->fail(RFB_ERR_ARG, "rfb_laswp_range: null matrix");
+    if (ncols <= 0 || k1 <= k0) return RFB_OK;
+    T *A = A_root + k0 + col0 * lda;
+    if (use_lists) {
+        if (ctx->perm_dst == nullptr || (size_t)k1 > ctx->perm_cap)
+            return ctx->fail(RFB_ERR_ARG, "rfb_laswp_range: exchange lists missing");
+        return rfb_launch_laswp_lists<T>(ctx, A, ncols, lda, k0, k1);
+    }
+    if (!ipiv) return ctx->fail(RFB_ERR_ARG, "rfb_laswp_range: null ipiv");
+    return rfb_launch_laswp<T>(ctx, A, ncols, lda, ipiv + k0, k1 - k0, k0);
 }
 
 template <typename T>
@@ -226,7 +261,8 @@ int rfb_create(rfb_ctx **out, int device) {
     if (prop.major != 10)
         return ctx->fail(RFB_ERR_UNSUPPORTED, "device %d is sm_%d%d; librfb200 is built for sm_100a only", device,
                          prop.major, prop.minor);
-    RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
     RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
     RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_stop));
@@ -258,14 +294,16 @@ int rfb_destroy(rfb_ctx *ctx) {
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
     if (ctx->d_mat) cudaFree(ctx->d_mat);
-    if (ctx->perm_dst) cudaFree(ctx->perm_dst);
-    if (ctx->perm_src) cudaFree(ctx->perm_src);
-    if (ctx->perm_width) cudaFree(ctx->perm_width);
+    if (!ctx->perm_external) {
+        if (ctx->perm_dst) cudaFree(ctx->perm_dst);
+        if (ctx->perm_src) cudaFree(ctx->perm_src);
+        if (ctx->perm_width) cudaFree(ctx->perm_width);
+    }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return RFB_OK;
@@ -292,6 +330,54 @@ int rfb_set_default_opts(rfb_ctx *ctx, const rfb_opts *opts) {
 int rfb_lu_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
                const rfb_opts *opts) {
     return lu_entry<double>(ctx, A, m, n, lda, ipiv, info, opts);
+}
+
+int rfb_lu_range_f64(rfb_ctx *ctx, double *A_root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv_dev,
+                     int64_t *info_dev, const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    return lu_range<double>(ctx, A_root, m, lda, c0, n, ipiv_dev, info_dev, opts);
+}
+int rfb_lu_range_f32(rfb_ctx *ctx, float *A_root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv_dev,
+                     int64_t *info_dev, const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    return lu_range<float>(ctx, A_root, m, lda, c0, n, ipiv_dev, info_dev, opts);
+}
+int rfb_laswp_range_f64(rfb_ctx *ctx, double *A_root, int64_t lda, int64_t col0, int64_t ncols, int64_t k0, int64_t k1,
+                        const int64_t *ipiv_dev, int use_lists) {
+    if (!ctx) return RFB_ERR_ARG;
+    return laswp_range<double>(ctx, A_root, lda, col0, ncols, k0, k1, ipiv_dev, use_lists);
+}
+int rfb_laswp_range_f32(rfb_ctx *ctx, float *A_root, int64_t lda, int64_t col0, int64_t ncols, int64_t k0, int64_t k1,
+                        const int64_t *ipiv_dev, int use_lists) {
+    if (!ctx) return RFB_ERR_ARG;
+    return laswp_range<float>(ctx, A_root, lda, col0, ncols, k0, k1, ipiv_dev, use_lists);
+}
+int rfb_perm_buffers(rfb_ctx *ctx, int32_t *dst_dev, int32_t *src_dev, int32_t *width_dev, int64_t cap) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (!dst_dev || !src_dev || !width_dev || cap <= 0) return ctx->fail(RFB_ERR_ARG, "rfb_perm_buffers: null buffer or cap <= 0");
+    if (!ctx->perm_external) {
+        cudaFree(ctx->perm_dst); cudaFree(ctx->perm_src); cudaFree(ctx->perm_width);
+    }
+    ctx->perm_dst = dst_dev; ctx->perm_src = src_dev; ctx->perm_width = width_dev;
+    ctx->perm_cap = (size_t)cap;
+    ctx->perm_external = true;
+    RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_dst, 0xFF, 2 * (size_t)cap * sizeof(int), ctx->stream));
+    RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_src, 0xFF, 2 * (size_t)cap * sizeof(int), ctx->stream));
+    RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_width, 0, (size_t)cap * sizeof(int), ctx->stream));
+    return RFB_OK;
+}
+int rfb_copy2d(rfb_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch, size_t width_bytes,
+               size_t height) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (width_bytes == 0 || height == 0) return RFB_OK;
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(dst_dev, dpitch, src_dev, spitch, width_bytes, height, cudaMemcpyDeviceToDevice, ctx->stream));
+    return RFB_OK;
+}
+int rfb_set_stream(rfb_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return RFB_ERR_ARG;
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return RFB_OK;
 }
 int rfb_lu_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
                const rfb_opts *opts) {

@@ -39,7 +39,8 @@ struct rfb_ctx {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     size_t mem_bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // stream everything is enqueued on
+    cudaStream_t own_stream = nullptr;    // the stream created with the context
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_sync = nullptr;
     std::string last_error;
@@ -57,6 +58,7 @@ struct rfb_ctx {
     // per-panel row-exchange lists written by K1 and consumed by the list-driven K2 (absolute rows)
     int *perm_dst = nullptr, *perm_src = nullptr, *perm_width = nullptr;
     size_t perm_cap = 0;                  // columns the three arrays are sized for
+    bool perm_external = false;           // arrays belong to the caller (rfb_perm_buffers)
 
     std::vector<cudaEvent_t> up_events;   // upload-chunk events of host-mode calls (reused)
 

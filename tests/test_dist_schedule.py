@@ -1,0 +1,130 @@
+"""CPU (gloo, world_size 2 and 3) tests of the multi-GPU schedule.
+
+The product's distributed recursion (`run_schedule` in recursivefactorization.jl_b200/dist_lu.py) is
+host logic over a backend interface; here it is driven by a numpy backend whose kernels are the CPU
+oracle's loops and whose broadcast is torch.distributed/gloo, and the gathered result must equal the
+single-process oracle factorization (pivots exactly, factors to rounding)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class NumpyBackend:
+    """Replicated-L 1-D block-cyclic LU on numpy arrays (one per rank), gloo broadcasts."""
+
+    def __init__(self, a_full, nb, rank, world):
+        from oracle import rf_oracle as O
+        self.O = O
+        self.n, self.nb, self.rank, self.world = a_full.shape[0], nb, rank, world
+        self.A = np.zeros_like(a_full, order="F")          # only own block columns are filled in
+        for j in range((self.n + nb - 1) // nb):
+            if j % world == rank:
+                self.A[:, j * nb:(j + 1) * nb] = a_full[:, j * nb:(j + 1) * nb]
+        self.ipiv = np.zeros(self.n, dtype=np.int64)
+        self.info = 0
+        self.bcasts = 0
+
+    def factor_block(self, c0, w):
+        sub = np.asfortranarray(self.A[c0:, c0:c0 + w])
+        f, p, info = self.O.lu_c(sub)
+        self.A[c0:, c0:c0 + w] = f
+        self.ipiv[c0:c0 + w] = p + c0
+        if info and not self.info:
+            self.info = info + c0
+
+    def bcast_block(self, c0, w, root):
+        panel = torch.from_numpy(np.ascontiguousarray(self.A[c0:, c0:c0 + w]))
+        piv = torch.from_numpy(self.ipiv[c0:c0 + w].copy())
+        dist.broadcast(panel, src=root)
+        dist.broadcast(piv, src=root)
+        self.bcasts += 1
+        if self.rank != root:
+            self.A[c0:, c0:c0 + w] = panel.numpy()
+            self.ipiv[c0:c0 + w] = piv.numpy()
+
+    def swap(self, col0, ncols, k0, k1):
+        blk = self.A[:, col0:col0 + ncols]
+        for i in range(k0, k1):
+            r = int(self.ipiv[i]) - 1
+            if r != i:
+                blk[[i, r], :] = blk[[r, i], :]
+
+    def trsm(self, c0, n1, col0, ncols):
+        import scipy.linalg as sl
+        l = self.A[c0:c0 + n1, c0:c0 + n1]
+        self.A[c0:c0 + n1, col0:col0 + ncols] = sl.solve_triangular(l, self.A[c0:c0 + n1, col0:col0 + ncols], lower=True,
+                                                                     unit_diagonal=True)
+
+    def gemm(self, c0, n1, col0, ncols):
+        self.A[c0 + n1:, col0:col0 + ncols] -= self.A[c0 + n1:, c0:c0 + n1] @ self.A[c0:c0 + n1, col0:col0 + ncols]
+
+
+def _worker(rank, world, port, n, nb, seed, zero_col, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import rfb200
+    from rfb200.dist_lu import run_schedule, owner_of, block_range
+    a = np.asfortranarray(np.random.default_rng(seed).random((n, n)))
+    if zero_col >= 0:
+        a[:, zero_col] = 0
+    be = NumpyBackend(a, nb, rank, world)
+    run_schedule(be, n, nb, rank, world)
+    # gather: every rank contributes its own block columns
+    full = torch.zeros((n, n), dtype=torch.float64)
+    for j in range((n + nb - 1) // nb):
+        if owner_of(j, world) == rank:
+            c0, w = block_range(j, n, nb)
+            full[:, c0:c0 + w] = torch.from_numpy(np.ascontiguousarray(be.A[:, c0:c0 + w]))
+    dist.all_reduce(full)
+    info = torch.tensor([be.info if be.info else 1 << 60])
+    dist.all_reduce(info, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "out.npz"), f=full.numpy(), ipiv=be.ipiv, info=int(info) if int(info) < (1 << 60) else 0,
+                 bcasts=be.bcasts)
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,n,nb,zero_col", [(2, 256, 64, -1), (2, 300, 64, -1), (3, 448, 64, -1), (2, 256, 64, 100)])
+def test_block_cyclic_schedule_matches_oracle(tmp_path, world, n, nb, zero_col):
+    sys.path.insert(0, ROOT)
+    from oracle import rf_oracle as O
+    mp.spawn(_worker, args=(world, _free_port(), n, nb, 5, zero_col, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "out.npz"))
+    a = np.asfortranarray(np.random.default_rng(5).random((n, n)))
+    if zero_col >= 0:
+        a[:, zero_col] = 0
+    want_f, want_p, want_info = O.lu_c(a.copy(order="F"))
+    assert int(got["info"]) == want_info
+    assert np.array_equal(got["ipiv"], want_p)                   # bit-exact pivots
+    assert int(got["bcasts"]) == (n + nb - 1) // nb              # one broadcast per block column
+    if want_info == 0:
+        assert np.allclose(got["f"], want_f, rtol=0, atol=20 * n * np.finfo(np.float64).eps * max(1.0, np.abs(want_f).max()))
+        assert O.residual_inf(a, np.asfortranarray(got["f"]), got["ipiv"]) < 20 * n * np.finfo(np.float64).eps
+
+
+def test_ownership_helpers():
+    sys.path.insert(0, ROOT)
+    import rfb200
+    from rfb200.dist_lu import block_range, owned_blocks, owner_of
+    assert [owner_of(j, 8) for j in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
+    assert owned_blocks(1, 4, 1000, 128) == [1, 5]
+    assert block_range(7, 1000, 128) == (896, 104)
+    assert sum(block_range(j, 1000, 128)[1] for j in range(8)) == 1000
