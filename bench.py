@@ -341,9 +341,10 @@ def run_ours_dist(args, rank, world, local_rank):
     pristine = {j: host_in[j].to(d.device) for j in d.my_blocks}
 
     def restore():
-        d.A.zero_()
-        for j in d.my_blocks:
-            slices[j].copy_(pristine[j])
+        with torch.cuda.stream(d.stream):
+            d.A.zero_()
+            for j in d.my_blocks:
+                slices[j].copy_(pristine[j])
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
@@ -365,9 +366,9 @@ def run_ours_dist(args, rank, world, local_rank):
         restore()
         torch.cuda.synchronize()
         dist.barrier()
-        e0.record()
+        e0.record(d.stream)
         d.factor()
-        e1.record()
+        e1.record(d.stream)
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     dist.barrier()
@@ -417,15 +418,18 @@ def run_ours_dist(args, rank, world, local_rank):
     if not args.skip_e2e:
         et = []
         for it in range(1 + min(args.steps, 2)):
-            d.A.zero_()
+            with torch.cuda.stream(d.stream):
+                d.A.zero_()
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
-            for j in d.my_blocks:
-                slices[j].copy_(host_in[j], non_blocking=True)
+            with torch.cuda.stream(d.stream):
+                for j in d.my_blocks:
+                    slices[j].copy_(host_in[j], non_blocking=True)
             d.factor()
-            for j in d.my_blocks:
-                host_out[j].copy_(slices[j], non_blocking=True)
+            with torch.cuda.stream(d.stream):
+                for j in d.my_blocks:
+                    host_out[j].copy_(slices[j], non_blocking=True)
             torch.cuda.synchronize()
             dist.barrier()
             if it > 0:
@@ -464,7 +468,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="matrix size (default 16384 on 1 GPU, 32768 distributed)")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=0, help="matrix size (default 16384 on 1 GPU, 32768 distributed)")
     ap.add_argument("--block", type=int, default=512, help="block-column width of the multi-GPU distribution")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--skip-cpu-baseline", action="store_true")

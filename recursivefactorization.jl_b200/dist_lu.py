@@ -54,29 +54,50 @@ def run_schedule(be, n: int, nb: int, rank: int, world: int) -> None:
     """
     nblk = (n + nb - 1) // nb
 
-    def rec(b0: int, nbk: int) -> None:
+    def leaf(b: int) -> None:
+        c0, width = block_range(b, n, nb)
+        root = owner_of(b, world)
+        if rank == root:
+            be.factor_block(c0, width)
+        be.bcast_block(c0, width, root)
+
+    def update(j: int, c0: int, n1: int) -> None:              # src/lu.jl:233-240 on one owned block column
+        col0, ncols = block_range(j, n, nb)
+        be.swap(col0, ncols, c0, c0 + n1)
+        be.trsm(c0, n1, col0, ncols)
+        be.gemm(c0, n1, col0, ncols)
+
+    def rec(b0: int, nbk: int, first_done: bool) -> None:
+        """`first_done`: the leftmost block column of this range was already factored (look-ahead)."""
+        if nbk == 1:
+            if not first_done:
+                leaf(b0)
+            return
         c0 = b0 * nb
         width = min(n, (b0 + nbk) * nb) - c0
-        if nbk == 1:
-            root = owner_of(b0, world)
-            if rank == root:
-                be.factor_block(c0, width)
-            be.bcast_block(c0, width, root)
-            return
         nb1 = (nbk + 1) // 2
         n1 = nb1 * nb
-        rec(b0, nb1)                                           # src/lu.jl:229
-        for j in range(b0 + nb1, b0 + nbk):                    # :233-240 on the columns this rank owns
-            if owner_of(j, world) == rank:
-                col0, ncols = block_range(j, n, nb)
-                be.swap(col0, ncols, c0, c0 + n1)
-                be.trsm(c0, n1, col0, ncols)
-                be.gemm(c0, n1, col0, ncols)
-        rec(b0 + nb1, nbk - nb1)                               # :244
+        rec(b0, nb1, first_done)                               # src/lu.jl:229
+        # Look-ahead: the first block column of the right half is the next one on the critical path.
+        # Its owner updates it first and factors + broadcasts it at once, and only then updates its other
+        # columns; the other ranks do all their updates of this node while that factorization runs.
+        first = b0 + nb1
+        mine = [j for j in range(first, b0 + nbk) if owner_of(j, world) == rank]
+        if owner_of(first, world) == rank:
+            update(first, c0, n1)
+            leaf(first)
+            for j in mine:
+                if j != first:
+                    update(j, c0, n1)
+        else:
+            for j in mine:
+                update(j, c0, n1)
+            leaf(first)
+        rec(first, nbk - nb1, True)                            # :244
         be.swap(c0, n1, c0 + n1, c0 + width)                   # :246 on the replicated L
 
     if nblk > 0:
-        rec(0, nblk)
+        rec(0, nblk, False)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -88,7 +109,7 @@ class DistributedLU:
     Usage (every rank, under torchrun):
         d = DistributedLU(n, np.float64, block=512)        # uses torch.distributed's default group
         d.set_block(j, host_array_n_by_w)   for j in d.my_blocks
-        d.factor()                                          # enqueued on torch's current stream
+        d.factor(); d.synchronize()                         # enqueued on d.stream
         info = d.info()                                     # global (all-reduced)
         d.get_block(j) / d.gather_to(0)
     """
@@ -106,9 +127,16 @@ class DistributedLU:
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
+        # make sure the (eagerly, asynchronously initialised) NCCL communicator is fully up before this
+        # process touches the device through a second CUDA runtime (librfb200 links cudart statically)
+        if self.world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize()
         self.ctx = ctx or Context(torch.cuda.current_device())
         self._lib, self._h = self.ctx._lib, self.ctx.handle
-        self.ctx._check(self._lib.rfb_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # one dedicated stream carries the kernels, the pack/unpack copies AND the NCCL broadcasts, in order
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.ctx._check(self._lib.rfb_set_stream(self._h, C.c_void_p(self.stream.cuda_stream)))
         tdt = torch.float64 if self.dtype == np.float64 else torch.float32
         self.item = self.dtype.itemsize
         self.A = torch.zeros(self.n * self.n, dtype=tdt, device=self.device)          # column-major, lda = n
@@ -129,6 +157,7 @@ class DistributedLU:
         self._laswp_range = getattr(self._lib, f"rfb_laswp_range_{suf}")
         self._trsm = getattr(self._lib, f"rfb_trsm_llnu_{suf}")
         self._gemm = getattr(self._lib, f"rfb_gemm_nn_sub_{suf}")
+        torch.cuda.synchronize()
 
     # -- data movement ----------------------------------------------------------------------------
     def _ptr(self, r: int, c: int) -> C.c_void_p:
@@ -138,11 +167,14 @@ class DistributedLU:
         c0, w = block_range(j, self.n, self.nb)
         assert host.shape == (self.n, w) and host.dtype == self.dtype
         t = self.torch.from_numpy(np.ascontiguousarray(host.T))           # w x n, rows = columns of A
-        self.A[c0 * self.n:(c0 + w) * self.n].copy_(t.reshape(-1), non_blocking=False)
+        with self.torch.cuda.stream(self.stream):
+            self.A[c0 * self.n:(c0 + w) * self.n].copy_(t.reshape(-1), non_blocking=False)
 
     def get_block(self, j: int) -> np.ndarray:
         c0, w = block_range(j, self.n, self.nb)
-        return np.asfortranarray(self.A[c0 * self.n:(c0 + w) * self.n].reshape(w, self.n).cpu().numpy().T)
+        with self.torch.cuda.stream(self.stream):
+            host = self.A[c0 * self.n:(c0 + w) * self.n].reshape(w, self.n).cpu()
+        return np.asfortranarray(host.numpy().T)
 
     # -- backend interface used by run_schedule -----------------------------------------------------
     def factor_block(self, c0: int, w: int) -> None:
@@ -190,30 +222,38 @@ class DistributedLU:
 
     # -- driver -------------------------------------------------------------------------------------
     def factor(self) -> None:
-        """Enqueue the whole distributed factorization on torch's current stream."""
-        self.info_dev.zero_()
-        self.p_dst.fill_(-1)
-        self.p_src.fill_(-1)
-        self.p_width.zero_()
-        run_schedule(self, self.n, self.nb, self.rank, self.world)
+        """Enqueue the whole distributed factorization on `self.stream` (no host synchronisation)."""
+        with self.torch.cuda.stream(self.stream):
+            self.info_dev.zero_()
+            self.p_dst.fill_(-1)
+            self.p_src.fill_(-1)
+            self.p_width.zero_()
+            run_schedule(self, self.n, self.nb, self.rank, self.world)
+
+    def synchronize(self) -> None:
+        self.stream.synchronize()
+        self.ctx.sync()
 
     def info(self) -> int:
         """Global info: smallest non-zero per-rank value (first zero-pivot column), else 0."""
-        t = self.info_dev[:1].clone()
         big = self.torch.iinfo(self.torch.int64).max
-        t = self.torch.where(t == 0, self.torch.full_like(t, big), t)
-        if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
-        v = int(t.item())
+        with self.torch.cuda.stream(self.stream):
+            t = self.info_dev[:1].clone()
+            t = self.torch.where(t == 0, self.torch.full_like(t, big), t)
+            if self.world > 1:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+            v = int(t.item())
         return 0 if v == big else v
 
     def pivots(self) -> np.ndarray:
-        return self.ipiv.cpu().numpy()
+        with self.torch.cuda.stream(self.stream):
+            return self.ipiv.cpu().numpy()
 
     def gather_to(self, dst: int = 0) -> Optional[np.ndarray]:
         """Assemble the factored matrix on rank `dst` (tests / small sizes only)."""
         out = np.empty((self.n, self.n), dtype=self.dtype, order="F") if self.rank == dst else None
         nblk = (self.n + self.nb - 1) // self.nb
+        self.synchronize()
         for j in range(nblk):
             c0, w = block_range(j, self.n, self.nb)
             root = owner_of(j, self.world)

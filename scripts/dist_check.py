@@ -36,9 +36,10 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(d.stream)
     d.factor()
-    e1.record()
+    e1.record(d.stream)
+    d.synchronize()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     info = d.info()
