@@ -337,12 +337,12 @@ def run_ours_dist(args, rank, world, local_rank):
         t.numpy()[:] = gen(j).reshape(-1, order="F")
         host_in[j] = t
         host_out[j] = torch.empty(n * w, dtype=torch.float64, pin_memory=True)
-        slices[j] = d.A[c0 * n:(c0 + w) * n]
+        slices[j] = d.block_slice(j)
     pristine = {j: host_in[j].to(d.device) for j in d.my_blocks}
 
     def restore():
         with torch.cuda.stream(d.stream):
-            d.A.zero_()
+            d.L.zero_()
             for j in d.my_blocks:
                 slices[j].copy_(pristine[j])
 
@@ -419,7 +419,7 @@ def run_ours_dist(args, rank, world, local_rank):
         et = []
         for it in range(1 + min(args.steps, 2)):
             with torch.cuda.stream(d.stream):
-                d.A.zero_()
+                d.L.zero_()
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()

@@ -251,6 +251,9 @@ __global__ void copy_kernel(double2 *__restrict__ dst, const double2 *__restrict
 
 }  // namespace
 
+// defined in gemm_tc32.cu
+int rfb_launch_gemm_f32_tc(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m, int64_t n, int64_t k,
+                           int64_t lda, bool *handled);
 // defined in gemm_tma.cu
 int rfb_launch_gemm_f64_tma(rfb_ctx *ctx, double *C, const double *A, const double *B, int64_t m, int64_t n,
                             int64_t k, int64_t lda, bool *handled);
@@ -278,8 +281,11 @@ template <>
 int rfb_launch_gemm<float>(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m, int64_t n,
                            int64_t k, int64_t lda, const rfb_opts *opts) {
     if (m <= 0 || n <= 0 || k <= 0) return RFB_OK;
-    if (opts && opts->f32_mode == RFB_F32_TF32X3)
-        return ctx->fail(RFB_ERR_UNSUPPORTED, "f32_mode TF32X3 (tcgen05) is not built yet; use RFB_F32_FP32");
+    if (opts && opts->f32_mode == RFB_F32_TF32X3) {
+        bool handled = false;
+        RFB_TRY(rfb_launch_gemm_f32_tc(ctx, C, A, B, m, n, k, lda, &handled));
+        if (handled) return RFB_OK;     // unaligned views fall through to the exact FFMA tiles
+    }
     dim3 grid((unsigned int)((m + SBM - 1) / SBM), (unsigned int)((n + SBN - 1) / SBN));
     RfbLaunchScope scope(ctx, RFB_KC_GEMM, 2.0 * (double)m * (double)n * (double)k);
     gemm_f32_simt_kernel<<<grid, STHREADS, 0, ctx->stream>>>(C, A, B, (int)m, (int)n, (int)k, lda);

@@ -48,9 +48,11 @@ def run_schedule(be, n: int, nb: int, rank: int, world: int) -> None:
 
     factor_block(c0, w)              owner only: LU of columns [c0, c0+w), rows c0.. (global pivots)
     bcast_block(c0, w, root)         everyone: panel rows c0.., its pivots (and exchange lists)
-    swap(col0, ncols, k0, k1)        pivots [k0, k1) applied to columns [col0, col0+ncols), rows >= k0
-    trsm(c0, n1, col0, ncols)        A[c0:c0+n1, cols] <- unitlower(A[c0:c0+n1, c0:c0+n1])^-1 A[c0:c0+n1, cols]
-    gemm(c0, n1, col0, ncols)        A[c0+n1:, cols] -= A[c0+n1:, c0:c0+n1] A[c0:c0+n1, cols]
+    update(blocks, c0, n1)           src/lu.jl:233-240 on the OWNED block columns `blocks` (ascending, hence
+                                     contiguous in the rank's local storage): row swaps with pivots [c0, c0+n1),
+                                     A12 <- L11^-1 A12, A22 -= L21 A12, with L11/L21 = columns [c0, c0+n1) of the replica
+    swap_left(c0, n1, k0, k1)        src/lu.jl:246: pivots [k0, k1) applied to rows >= k0 of columns [c0, c0+n1)
+                                     (the replicated L and the rank's own copy of those columns)
     """
     nblk = (n + nb - 1) // nb
 
@@ -60,12 +62,6 @@ def run_schedule(be, n: int, nb: int, rank: int, world: int) -> None:
         if rank == root:
             be.factor_block(c0, width)
         be.bcast_block(c0, width, root)
-
-    def update(j: int, c0: int, n1: int) -> None:              # src/lu.jl:233-240 on one owned block column
-        col0, ncols = block_range(j, n, nb)
-        be.swap(col0, ncols, c0, c0 + n1)
-        be.trsm(c0, n1, col0, ncols)
-        be.gemm(c0, n1, col0, ncols)
 
     def rec(b0: int, nbk: int, first_done: bool) -> None:
         """`first_done`: the leftmost block column of this range was already factored (look-ahead)."""
@@ -84,17 +80,17 @@ def run_schedule(be, n: int, nb: int, rank: int, world: int) -> None:
         first = b0 + nb1
         mine = [j for j in range(first, b0 + nbk) if owner_of(j, world) == rank]
         if owner_of(first, world) == rank:
-            update(first, c0, n1)
+            be.update([first], c0, n1)
             leaf(first)
-            for j in mine:
-                if j != first:
-                    update(j, c0, n1)
+            rest = [j for j in mine if j != first]
+            if rest:
+                be.update(rest, c0, n1)
         else:
-            for j in mine:
-                update(j, c0, n1)
+            if mine:
+                be.update(mine, c0, n1)
             leaf(first)
         rec(first, nbk - nb1, True)                            # :244
-        be.swap(c0, n1, c0 + n1, c0 + width)                   # :246 on the replicated L
+        be.swap_left(c0, n1, c0 + n1, c0 + width)              # :246
 
     if nblk > 0:
         rec(0, nblk, False)
@@ -139,7 +135,18 @@ class DistributedLU:
         self.ctx._check(self._lib.rfb_set_stream(self._h, C.c_void_p(self.stream.cuda_stream)))
         tdt = torch.float64 if self.dtype == np.float64 else torch.float32
         self.item = self.dtype.itemsize
-        self.A = torch.zeros(self.n * self.n, dtype=tdt, device=self.device)          # column-major, lda = n
+        self.my_blocks = owned_blocks(self.rank, self.world, self.n, self.nb)
+        self.lcol = {}                                  # block -> first local column (own blocks are stored compactly)
+        ncl = 0
+        for j in self.my_blocks:
+            self.lcol[j] = ncl
+            ncl += block_range(j, self.n, self.nb)[1]
+        self.ncols_local = ncl
+        # two column-major buffers with the SAME leading dimension n, so one kernel call can mix them:
+        #   L   : full-size replica, valid where L panels were received (rows >= diagonal block)
+        #   A   : this rank's own block columns, compact, in block order
+        self.L = torch.zeros(self.n * self.n, dtype=tdt, device=self.device)
+        self.A = torch.zeros(self.n * max(ncl, 1), dtype=tdt, device=self.device)
         self.ipiv = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self.info_dev = torch.zeros(8, dtype=torch.int64, device=self.device)
         self.p_dst = torch.empty(2 * self.n + 128, dtype=torch.int32, device=self.device)
@@ -150,7 +157,6 @@ class DistributedLU:
         meta = self.nb * (8 + 8 + 8 + 4)
         self.stage = torch.empty(self.n * self.nb * self.item + meta + 256, dtype=torch.uint8, device=self.device)
         self.opts = _make_opts(_lib.RFB_MEM_DEVICE, leaf_width)
-        self.my_blocks = owned_blocks(self.rank, self.world, self.n, self.nb)
         self.bcast_bytes = 0
         suf = "f64" if self.dtype == np.float64 else "f32"
         self._lu_range = getattr(self._lib, f"rfb_lu_range_{suf}")
@@ -160,25 +166,35 @@ class DistributedLU:
         torch.cuda.synchronize()
 
     # -- data movement ----------------------------------------------------------------------------
-    def _ptr(self, r: int, c: int) -> C.c_void_p:
-        return C.c_void_p(self.A.data_ptr() + (r + c * self.n) * self.item)
+    def _pa(self, r: int, lc: int) -> C.c_void_p:        # own storage, local column lc
+        return C.c_void_p(self.A.data_ptr() + (r + lc * self.n) * self.item)
+
+    def _pl(self, r: int, c: int) -> C.c_void_p:         # replica, global column c
+        return C.c_void_p(self.L.data_ptr() + (r + c * self.n) * self.item)
+
+    def block_slice(self, j: int):
+        lc, w = self.lcol[j], block_range(j, self.n, self.nb)[1]
+        return self.A[lc * self.n:(lc + w) * self.n]
 
     def set_block(self, j: int, host: np.ndarray) -> None:
         c0, w = block_range(j, self.n, self.nb)
         assert host.shape == (self.n, w) and host.dtype == self.dtype
         t = self.torch.from_numpy(np.ascontiguousarray(host.T))           # w x n, rows = columns of A
         with self.torch.cuda.stream(self.stream):
-            self.A[c0 * self.n:(c0 + w) * self.n].copy_(t.reshape(-1), non_blocking=False)
+            self.block_slice(j).copy_(t.reshape(-1), non_blocking=False)
 
     def get_block(self, j: int) -> np.ndarray:
-        c0, w = block_range(j, self.n, self.nb)
+        w = block_range(j, self.n, self.nb)[1]
         with self.torch.cuda.stream(self.stream):
-            host = self.A[c0 * self.n:(c0 + w) * self.n].reshape(w, self.n).cpu()
+            host = self.block_slice(j).reshape(w, self.n).cpu()
         return np.asfortranarray(host.numpy().T)
 
     # -- backend interface used by run_schedule -----------------------------------------------------
     def factor_block(self, c0: int, w: int) -> None:
-        self.ctx._check(self._lu_range(self._h, C.c_void_p(self.A.data_ptr()), self.n, self.n, c0, w,
+        # the block lives at local column lc: shift the base so that (row c0, col c0) of the "root" view is it
+        lc = self.lcol[c0 // self.nb]
+        root = self.A.data_ptr() + (lc - c0) * self.n * self.item
+        self.ctx._check(self._lu_range(self._h, C.c_void_p(root), self.n, self.n, c0, w,
                                        C.c_void_p(self.ipiv.data_ptr()), C.c_void_p(self.info_dev.data_ptr()),
                                        C.byref(self.opts)))
 
@@ -189,8 +205,9 @@ class DistributedLU:
         off_piv, off_dst, off_src, off_w = pbytes, pbytes + 8 * w, pbytes + 16 * w, pbytes + 24 * w
         total = pbytes + 28 * w
         lib, h = self._lib, self._h
-        if self.rank == root:                                             # pack
-            self.ctx._check(lib.rfb_copy2d(h, C.c_void_p(st), rows * self.item, self._ptr(c0, c0), self.n * self.item,
+        if self.rank == root:                                             # pack from the own storage
+            lc = self.lcol[c0 // self.nb]
+            self.ctx._check(lib.rfb_copy2d(h, C.c_void_p(st), rows * self.item, self._pa(c0, lc), self.n * self.item,
                                            rows * self.item, w))
             self.ctx._check(lib.rfb_d2d(h, C.c_void_p(st + off_piv), C.c_void_p(self.ipiv.data_ptr() + 8 * c0), 8 * w))
             self.ctx._check(lib.rfb_d2d(h, C.c_void_p(st + off_dst), C.c_void_p(self.p_dst.data_ptr() + 8 * c0), 8 * w))
@@ -200,25 +217,36 @@ class DistributedLU:
             self.dist.broadcast(self.stage[:total], src=self.dist.get_global_rank(self.group, root) if self.group else root,
                                 group=self.group)
             self.bcast_bytes += total
-        if self.rank != root:                                             # unpack
-            self.ctx._check(lib.rfb_copy2d(h, self._ptr(c0, c0), self.n * self.item, C.c_void_p(st), rows * self.item,
-                                           rows * self.item, w))
+        # every rank (the owner too) unpacks the panel into its replica
+        self.ctx._check(lib.rfb_copy2d(h, self._pl(c0, c0), self.n * self.item, C.c_void_p(st), rows * self.item,
+                                       rows * self.item, w))
+        if self.rank != root:
             self.ctx._check(lib.rfb_d2d(h, C.c_void_p(self.ipiv.data_ptr() + 8 * c0), C.c_void_p(st + off_piv), 8 * w))
             self.ctx._check(lib.rfb_d2d(h, C.c_void_p(self.p_dst.data_ptr() + 8 * c0), C.c_void_p(st + off_dst), 8 * w))
             self.ctx._check(lib.rfb_d2d(h, C.c_void_p(self.p_src.data_ptr() + 8 * c0), C.c_void_p(st + off_src), 8 * w))
             self.ctx._check(lib.rfb_d2d(h, C.c_void_p(self.p_width.data_ptr() + 4 * c0), C.c_void_p(st + off_w), 4 * w))
 
-    def swap(self, col0: int, ncols: int, k0: int, k1: int) -> None:
-        self.ctx._check(self._laswp_range(self._h, C.c_void_p(self.A.data_ptr()), self.n, col0, ncols, k0, k1,
-                                          C.c_void_p(self.ipiv.data_ptr()), 1))
+    def _local_range(self, blocks):
+        lc0 = self.lcol[blocks[0]]
+        ncols = sum(block_range(j, self.n, self.nb)[1] for j in blocks)
+        return lc0, ncols
 
-    def trsm(self, c0: int, n1: int, col0: int, ncols: int) -> None:
-        self.ctx._check(self._trsm(self._h, self._ptr(c0, c0), n1, self._ptr(c0, col0), ncols, self.n))
-
-    def gemm(self, c0: int, n1: int, col0: int, ncols: int) -> None:
+    def update(self, blocks, c0: int, n1: int) -> None:
+        lc0, ncols = self._local_range(blocks)
+        base = C.c_void_p(self.A.data_ptr())
+        # row swaps on the own columns (a "root" view whose column index is the local one)
+        self.ctx._check(self._laswp_range(self._h, base, self.n, lc0, ncols, c0, c0 + n1, C.c_void_p(self.ipiv.data_ptr()), 1))
+        self.ctx._check(self._trsm(self._h, self._pl(c0, c0), n1, self._pa(c0, lc0), ncols, self.n))
         m2 = self.n - c0 - n1
-        self.ctx._check(self._gemm(self._h, self._ptr(c0 + n1, col0), self._ptr(c0 + n1, c0), self._ptr(c0, col0),
-                                   m2, ncols, n1, self.n))
+        self.ctx._check(self._gemm(self._h, self._pa(c0 + n1, lc0), self._pl(c0 + n1, c0), self._pa(c0, lc0), m2, ncols, n1, self.n))
+
+    def swap_left(self, c0: int, n1: int, k0: int, k1: int) -> None:
+        piv = C.c_void_p(self.ipiv.data_ptr())
+        self.ctx._check(self._laswp_range(self._h, C.c_void_p(self.L.data_ptr()), self.n, c0, n1, k0, k1, piv, 1))
+        mine = [j for j in self.my_blocks if c0 <= j * self.nb < c0 + n1]
+        if mine:
+            lc0, ncols = self._local_range(mine)
+            self.ctx._check(self._laswp_range(self._h, C.c_void_p(self.A.data_ptr()), self.n, lc0, ncols, k0, k1, piv, 1))
 
     # -- driver -------------------------------------------------------------------------------------
     def factor(self) -> None:
@@ -257,14 +285,14 @@ class DistributedLU:
         for j in range(nblk):
             c0, w = block_range(j, self.n, self.nb)
             root = owner_of(j, self.world)
-            buf = self.A[c0 * self.n:(c0 + w) * self.n]
+            buf = self.block_slice(j) if self.rank == root else None
             if root == dst:
                 if self.rank == dst:
                     out[:, c0:c0 + w] = self.get_block(j)
             elif self.rank == root:
                 self.dist.send(buf, dst=dst, group=self.group)
             elif self.rank == dst:
-                tmp = self.torch.empty_like(buf)
+                tmp = self.torch.empty(self.n * w, dtype=self.A.dtype, device=self.device)
                 self.dist.recv(tmp, src=root, group=self.group)
                 out[:, c0:c0 + w] = tmp.reshape(w, self.n).cpu().numpy().T
         return out

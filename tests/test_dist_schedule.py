@@ -50,21 +50,27 @@ class NumpyBackend:
             self.A[c0:, c0:c0 + w] = panel.numpy()
             self.ipiv[c0:c0 + w] = piv.numpy()
 
-    def swap(self, col0, ncols, k0, k1):
+    def _swap(self, col0, ncols, k0, k1):
         blk = self.A[:, col0:col0 + ncols]
         for i in range(k0, k1):
             r = int(self.ipiv[i]) - 1
             if r != i:
                 blk[[i, r], :] = blk[[r, i], :]
 
-    def trsm(self, c0, n1, col0, ncols):
+    def update(self, blocks, c0, n1):
         import scipy.linalg as sl
-        l = self.A[c0:c0 + n1, c0:c0 + n1]
-        self.A[c0:c0 + n1, col0:col0 + ncols] = sl.solve_triangular(l, self.A[c0:c0 + n1, col0:col0 + ncols], lower=True,
-                                                                     unit_diagonal=True)
+        assert all(b % self.world == self.rank for b in blocks) and blocks == sorted(blocks)
+        for j in blocks:
+            col0 = j * self.nb
+            ncols = min(self.n, col0 + self.nb) - col0
+            self._swap(col0, ncols, c0, c0 + n1)
+            l = self.A[c0:c0 + n1, c0:c0 + n1]
+            self.A[c0:c0 + n1, col0:col0 + ncols] = sl.solve_triangular(l, self.A[c0:c0 + n1, col0:col0 + ncols], lower=True,
+                                                                         unit_diagonal=True)
+            self.A[c0 + n1:, col0:col0 + ncols] -= self.A[c0 + n1:, c0:c0 + n1] @ self.A[c0:c0 + n1, col0:col0 + ncols]
 
-    def gemm(self, c0, n1, col0, ncols):
-        self.A[c0 + n1:, col0:col0 + ncols] -= self.A[c0 + n1:, c0:c0 + n1] @ self.A[c0:c0 + n1, col0:col0 + ncols]
+    def swap_left(self, c0, n1, k0, k1):
+        self._swap(c0, n1, k0, k1)
 
 
 def _worker(rank, world, port, n, nb, seed, zero_col, out_dir):

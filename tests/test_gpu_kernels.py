@@ -195,3 +195,33 @@ def test_gemm_linearity_large(ctx):
     want = big[k:, k:] @ x - big[k:, :k] @ (big[:k, k:] @ x)
     assert np.allclose(got[k:, k:] @ x, want, rtol=1e-10, atol=1e-8)
     d.free()
+
+
+# ---- K4' Float32 on tcgen05 (3xTF32) -------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(128, 128, 32), (128, 128, 8), (256, 384, 96), (1000, 520, 300), (2048, 2048, 64),
+                                   (1536, 1024, 1024), (4096, 4096, 512)])
+def test_gemm_f32_tcgen05_matches_oracle(ctx, shape):
+    """tcgen05.mma kind::tf32 with the 3-term split must be FP32-accurate: compared with the exact-FP32
+    oracle loop at a tolerance of a few k*eps(Float32) (plain TF32 would be ~1000x worse)."""
+    m, n, k = shape
+    k4 = (k + 3) // 4 * 4
+    rng = np.random.default_rng([44, m, n, k])
+    lda = (k4 + m + 3) // 4 * 4
+    big = rand_matrix(rng, lda, k4 + n, np.float32)
+    c_off, a_off, b_off = (k4, k4), (k4, 0), (0, k4)
+    want = O.schur_c(big.copy(order="F"), c_off, a_off, b_off, m, n, k, threads=4)
+    d = Dev(ctx, big)
+    ctx.set_default_opts(f32_mode=1)
+    try:
+        before = ctx.profile_read()["gemm"]["launches"]
+        ctx._check(ctx._lib.rfb_gemm_nn_sub_f32(ctx.handle, d.at(*c_off), d.at(*a_off), d.at(*b_off), m, n, k, d.lda))
+        got = d.get()
+    finally:
+        ctx.set_default_opts()
+    tol = 4 * k * float(np.finfo(np.float32).eps) * max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    assert err <= tol, (err, tol)
+    untouched = np.ones_like(big, dtype=bool)
+    untouched[c_off[0]:c_off[0] + m, c_off[1]:c_off[1] + n] = False
+    assert np.array_equal(got[untouched], big[untouched])
+    d.free()

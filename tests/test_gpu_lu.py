@@ -157,3 +157,15 @@ def test_baseline_config_16384_properties(ctx):
     assert np.all(np.abs(np.tril(F.factors, -1)) <= 1.0)
     res = hutchinson_residual(a0, F.factors, F.ipiv)
     assert res <= 20 * n * np.finfo(np.float64).eps, res
+
+
+@pytest.mark.parametrize("n", [512, 2048, 4096])
+def test_f32_tensor_core_mode(ctx, n):
+    """Float32 LU with the trailing update on tcgen05 (f32_mode = TF32X3): the reference's own bound
+    20*n*eps(Float32) must hold, and pivots may differ from the FP32 oracle only at proven near-ties."""
+    a0 = np.asfortranarray(np.random.default_rng([12, n]).random((n, n), dtype=np.float32))
+    _, want_p, _ = O.lu_c(a0.copy(order="F"), threads=8)
+    F = rfb200.lu(a0, ctx=ctx, f32_mode=1)
+    assert F.info == 0
+    assert_pivots_match(a0, F.factors, F.ipiv, want_p, strict=False)
+    assert_testlu(a0, F.factors, F.ipiv, F.info, 0)
