@@ -9,7 +9,7 @@
 //
 // Warp roles (192 threads, one 128 x 128 output tile per CTA, 3-stage ring of K = 32 slices):
 //   warp 0      TMA producer: A slice as four [32 k][32 m] boxes (A is column-major => MN-major
-//               operand), B slice as one [128 n][32 k] box (K-major), both 128-byte swizzled
+//               operand, swizzle 128B_ATOM_32B), B slice as one [128 n][32 k] box (K-major, swizzle 128B)
 //   warps 2..5  split workers: rewrite hi in place, write lo to the twin buffers, fence to the async
 //               proxy, signal the MMA warp; afterwards the same warps are the epilogue
 //   warp 1      TMEM allocation + one elected lane issuing 12 tcgen05.mma per slice, tcgen05.commit
@@ -27,7 +27,7 @@ constexpr int CTHREADS = 192;
 constexpr int kTileBytes = CBM * CBK * 4;                       // 16 KB (A slice == B slice)
 constexpr int kStage = 4 * kTileBytes;                          // A_hi | B_hi | A_lo | B_lo
 constexpr size_t kTc32Smem = (size_t)CSTAGES * kStage + 1024 + 256;
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 256;   // two 128-column FP32 accumulators
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
@@ -57,13 +57,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 
 // shared-memory matrix descriptor (sm_100 format): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
-// version 1 << 46 | layout SWIZZLE_128B (2) << 61
-__device__ __forceinline__ unsigned long long make_desc(unsigned int saddr, unsigned int lbo, unsigned int sbo) {
+// version 1 << 46 | layout type << 61 (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ unsigned long long make_desc(unsigned int saddr, unsigned int lbo, unsigned int sbo,
+                                                        unsigned int layout) {
     unsigned long long d = (unsigned long long)((saddr & 0x3FFFFu) >> 4);
     d |= (unsigned long long)(lbo >> 4) << 16;
     d |= (unsigned long long)(sbo >> 4) << 32;
     d |= 1ull << 46;
-    d |= 2ull << 61;
+    d |= (unsigned long long)layout << 61;
     return d;
 }
 // instruction descriptor: D = F32, A = B = TF32, A MN-major (column-major A), B K-major, N = 128, M = 128
@@ -146,15 +147,21 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 const unsigned int a_hi = st, b_hi = st + kTileBytes, a_lo = st + 2 * kTileBytes, b_lo = st + 3 * kTileBytes;
 #pragma unroll
                 for (int ks = 0; ks < CBK / 8; ++ks) {
-                    // A (MN-major): k-step = next group of 8 k-rows (+1024 B); LBO = 4096 B between 32-row M chunks
-                    // B (K-major) : k-step = +32 B inside the 128-byte swizzled row; SBO = 1024 B between 8-row N groups
-                    const unsigned long long dah = make_desc(a_hi + ks * 1024, 4096, 1024);
-                    const unsigned long long dal = make_desc(a_lo + ks * 1024, 4096, 1024);
-                    const unsigned long long dbh = make_desc(b_hi + ks * 32, 16, 1024);
-                    const unsigned long long dbl = make_desc(b_lo + ks * 32, 16, 1024);
+                    // A (MN-major TF32: the only legal layout is SWIZZLE_128B_BASE32B, verified with
+                    //   scripts/umma_probe.cu): k-rows dense at 128 B, 32-byte chunks XOR-ed with k % 4;
+                    //   LBO = 4096 B between 32-row M chunks, SBO = 512 B between 4-row K groups, k-step = +1024 B
+                    // B (K-major, SWIZZLE_128B): k-step = +32 B inside the swizzled row; SBO = 1024 B between 8-row N groups
+                    const unsigned long long dah = make_desc(a_hi + ks * 1024, 4096, 512, 1);
+                    const unsigned long long dal = make_desc(a_lo + ks * 1024, 4096, 512, 1);
+                    const unsigned long long dbh = make_desc(b_hi + ks * 32, 16, 1024, 2);
+                    const unsigned long long dbl = make_desc(b_lo + ks * 32, 16, 1024, 2);
+                    // The tensor core adds into its FP32 accumulator with truncation, so every accumulation
+                    // step of a large running sum costs a biased half-ulp.  The big term and the two
+                    // correction terms (2^-11 smaller) therefore go to separate accumulators: the big sum is
+                    // touched once per k-step instead of three times and the small sum's truncation is negligible.
                     umma_tf32(tmem, dah, dbh, (kt | ks) != 0);
-                    umma_tf32(tmem, dal, dbh, 1u);
-                    umma_tf32(tmem, dah, dbl, 1u);
+                    umma_tf32(tmem + CBN, dal, dbh, (kt | ks) != 0);
+                    umma_tf32(tmem + CBN, dah, dbl, 1u);
                 }
                 umma_commit(&empty[s]);                  // slot reusable once these MMAs have read it
             }
@@ -191,12 +198,17 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const unsigned int taddr = tmem + ((unsigned int)(q * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < CBN; c0 += 16) {
-            unsigned int v[16];
+            unsigned int v[16], w[16];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                 : "r"(taddr + (unsigned int)c0) : "memory");
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                  "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                : "r"(taddr + (unsigned int)(CBN + c0)) : "memory");
             float cv[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
@@ -207,7 +219,7 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
                 const int c = n0 + c0 + u;
-                if (r < M && c < N) C[r + (long long)c * lda] = cv[u] - __uint_as_float(v[u]);
+                if (r < M && c < N) C[r + (long long)c * lda] = cv[u] - (__uint_as_float(v[u]) + __uint_as_float(w[u]));
             }
         }
     }
@@ -224,14 +236,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 bool make_map_f32(rfb_ctx *ctx, CUtensorMap *map, const float *ptr, uint64_t d0, uint64_t d1, uint64_t stride1_bytes,
-                  uint32_t box0, uint32_t box1) {
+                  uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
     cuuint64_t dims[2] = {d0, d1};
     cuuint64_t strides[1] = {stride1_bytes};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -243,8 +255,10 @@ int rfb_launch_gemm_f32_tc(rfb_ctx *ctx, float *C, const float *A, const float *
     if (!ctx->encode_tiled) return RFB_OK;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 3)) return RFB_OK;
     CUtensorMap mapA, mapB;
-    if (!make_map_f32(ctx, &mapA, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda * 4, 32, CBK)) return RFB_OK;
-    if (!make_map_f32(ctx, &mapB, B, (uint64_t)k, (uint64_t)n, (uint64_t)lda * 4, CBK, CBN)) return RFB_OK;
+    if (!make_map_f32(ctx, &mapA, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda * 4, 32, CBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return RFB_OK;
+    if (!make_map_f32(ctx, &mapB, B, (uint64_t)k, (uint64_t)n, (uint64_t)lda * 4, CBK, CBN, CU_TENSOR_MAP_SWIZZLE_128B))
+        return RFB_OK;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)gemm_f32_tc_kernel, kTc32Smem));
     const int tiles_m = (int)((m + CBM - 1) / CBM), tiles_n = (int)((n + CBN - 1) / CBN);
     RfbLaunchScope scope(ctx, RFB_KC_GEMM, 2.0 * (double)m * (double)n * (double)k);

@@ -201,8 +201,9 @@ def test_gemm_linearity_large(ctx):
 @pytest.mark.parametrize("shape", [(128, 128, 32), (128, 128, 8), (256, 384, 96), (1000, 520, 300), (2048, 2048, 64),
                                    (1536, 1024, 1024), (4096, 4096, 512)])
 def test_gemm_f32_tcgen05_matches_oracle(ctx, shape):
-    """tcgen05.mma kind::tf32 with the 3-term split must be FP32-accurate: compared with the exact-FP32
-    oracle loop at a tolerance of a few k*eps(Float32) (plain TF32 would be ~1000x worse)."""
+    """tcgen05.mma kind::tf32 with the 3-term split must be FP32-level accurate: within 0.5*k*eps(Float32)
+    of the exact-FP32 oracle loop (measured: 1.5-3x the FFMA kernel's own error, because the tensor core
+    accumulates with truncation; plain TF32 would miss this tolerance by ~20x)."""
     m, n, k = shape
     k4 = (k + 3) // 4 * 4
     rng = np.random.default_rng([44, m, n, k])
@@ -218,7 +219,7 @@ def test_gemm_f32_tcgen05_matches_oracle(ctx, shape):
         got = d.get()
     finally:
         ctx.set_default_opts()
-    tol = 4 * k * float(np.finfo(np.float32).eps) * max(1.0, float(np.abs(want).max()))
+    tol = 0.5 * max(k, 16) * float(np.finfo(np.float32).eps) * max(1.0, float(np.abs(want).max()))
     err = float(np.abs(got - want).max())
     assert err <= tol, (err, tol)
     untouched = np.ones_like(big, dtype=bool)
