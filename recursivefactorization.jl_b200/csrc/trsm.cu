@@ -50,6 +50,121 @@ trsm_diag_kernel(const T *__restrict__ L, int kb, T *__restrict__ B, long long n
     }
 }
 
+// Block solve for up to 256 x 256 triangles in ONE launch (left-looking over 64 x 64 sub-blocks).
+// A thread-per-column solve has only nrhs threads of parallelism (8192 columns = 1.7 warps per SM)
+// and crawls on exposed shared-memory latency, so the rows are split as well: a CTA of 8 warps
+// handles 32 right-hand-side columns (lane = column), warp g owns rows 8g..8g+7 of the current
+// 64-row sub-block in registers.  For sub-block row s: subtract the contributions of the solved
+// sub-blocks t < s (x_s -= L_st x_t; x_t stays in shared memory, L_st streams through a shared tile
+// whose successor is prefetched into registers during the FMAs), then solve the 64 x 64 diagonal
+// triangle in eight 8-row phases (owning warp solves its 8 x 8 triangle and publishes it, the warps
+// below update).  Replaces, per 256 rows, 4 diagonal launches + 3 half-empty small GEMM launches.
+constexpr int kSub = 64;
+constexpr int kBlkCols = 32;
+constexpr int kBlkThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kBlkThreads)
+trsm_block_kernel(const T *__restrict__ L, int kb, T *__restrict__ B, long long nrhs, long long lda) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sL = reinterpret_cast<T *>(smem_raw);                    // [64 cols][64 rows]
+    T *sX = sL + kSub * kSub;                                   // [4 sub-blocks][64 rows][32 cols]
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const long long col = (long long)blockIdx.x * kBlkCols + lane;
+    const bool active = col < nrhs;
+    T *xcol = B + (active ? col : 0) * lda;
+    const int nsub = (kb + kSub - 1) / kSub;
+    const int nblocks = nsub * (nsub + 1) / 2;
+
+    // L block idx -> (s, t <= s) in row-major order of s; each thread carries 16 elements of it
+    T tl[16];
+    auto fetch = [&](int idx) {
+        int s = 0, rem = idx;
+        while (rem > s) { rem -= s + 1; ++s; }
+        const int t = rem;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + kBlkThreads * i, r = e & 63, c = e >> 6;
+            const int gr = s * kSub + r, gc = t * kSub + c;
+            tl[i] = (gr < kb && gc < kb) ? L[gr + (long long)gc * lda] : T(0);
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + kBlkThreads * i;
+            sL[(e >> 6) * kSub + (e & 63)] = tl[i];
+        }
+    };
+
+    fetch(0);
+    int idx = 0;
+    for (int s = 0; s < nsub; ++s) {
+        const int r0 = s * kSub + 8 * g;
+        T x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = (active && r0 + q < kb) ? xcol[r0 + q] : T(0);
+        for (int t = 0; t <= s; ++t, ++idx) {
+            __syncthreads();                          // everyone is done with the previous L block
+            stash();
+            if (idx + 1 < nblocks) fetch(idx + 1);    // next block's loads fly during the FMAs below
+            __syncthreads();
+            if (t < s) {                              // x_s -= L_st x_t
+                const T *xt = sX + t * kSub * kBlkCols + lane;
+#pragma unroll 8
+                for (int j = 0; j < kSub; ++j) {
+                    const T nv = -xt[j * kBlkCols];
+                    const T *lj = sL + j * kSub + 8 * g;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = fma(lj[q], nv, x[q]);
+                }
+            } else {                                  // 64 x 64 diagonal triangle, eight 8-row phases
+                T *xs = sX + s * kSub * kBlkCols + lane;
+#pragma unroll 1
+                for (int p = 0; p < 8; ++p) {
+                    if (g == p) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const T nxc = -x[c];
+                            const T *lc = sL + (8 * p + c) * kSub + 8 * p;
+#pragma unroll
+                            for (int q = c + 1; q < 8; ++q) x[q] = fma(lc[q], nxc, x[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) xs[(8 * p + q) * kBlkCols] = x[q];
+                    }
+                    __syncthreads();
+                    if (g > p) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const T nv = -xs[(8 * p + c) * kBlkCols];
+                            const T *lc = sL + (8 * p + c) * kSub + 8 * g;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) x[q] = fma(lc[q], nv, x[q]);
+                        }
+                    }
+                }
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (r0 + q < kb) xcol[r0 + q] = x[q];
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+int launch_block(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
+    constexpr size_t smem = sizeof(T) * (kSub * kSub + 4 * kSub * kBlkCols);
+    auto kern = trsm_block_kernel<T>;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
+    RfbLaunchScope scope(ctx, RFB_KC_TRSM, (double)kb * (double)kb * (double)nrhs);
+    kern<<<(unsigned int)((nrhs + kBlkCols - 1) / kBlkCols), kBlkThreads, smem, ctx->stream>>>(L, kb, B, nrhs, lda);
+    RFB_CUDA(ctx, cudaGetLastError());
+    return RFB_OK;
+}
+
 template <typename T, int TB>
 int launch_diag(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
     constexpr int COLS = TB;
@@ -67,7 +182,8 @@ int trsm_rec(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t ld
              const rfb_opts *opts) {
     if (k <= tb) {
         if (tb == 32) return launch_diag<T, 32>(ctx, L, (int)k, B, nrhs, lda);
-        return launch_diag<T, 64>(ctx, L, (int)k, B, nrhs, lda);
+        if (tb == 64) return launch_diag<T, 64>(ctx, L, (int)k, B, nrhs, lda);
+        return launch_block<T>(ctx, L, (int)k, B, nrhs, lda);
     }
     // split at a multiple of the diagonal block nearest to k/2
     int64_t k1 = ((k / 2 + tb - 1) / tb) * tb;
@@ -83,7 +199,8 @@ template <typename T>
 int rfb_launch_trsm(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t lda,
                     const rfb_opts *opts) {
     if (k <= 0 || nrhs <= 0) return RFB_OK;
-    int tb = (opts && opts->trsm_block == 32) ? 32 : 64;
+    int tb = 256;                                    // default: fused 256-row block solve
+    if (opts && (opts->trsm_block == 32 || opts->trsm_block == 64 || opts->trsm_block == 128)) tb = opts->trsm_block;
     return trsm_rec<T>(ctx, L, k, B, nrhs, lda, tb, opts);
 }
 

@@ -64,7 +64,7 @@ out["gemm"] = res
 
 # ---- trsm -----------------------------------------------------------------------------------------
 res = {}
-for (k, nrhs) in [(64, 8192), (64, 1024), (128, 8192), (1024, 1024), (2048, 2048), (8192, 8192)]:
+for (k, nrhs) in [(64, 8192), (64, 1024), (128, 8192), (256, 8192), (256, 512), (1024, 1024), (2048, 2048), (8192, 8192)]:
     f = lambda: ctx._check(lib.rfb_trsm_llnu_f64(h, at(0, 0), k, at(0, N), nrhs, lda))
     t = timed(f, reps=2)
     res[f"{k}x{nrhs}"] = {"ms": round(t, 4), "tflops": round(1.0 * k * k * nrhs / t / 1e9, 2)}

@@ -139,7 +139,8 @@ def test_laswp_matches_oracle(ctx, dtype, shape):
 
 # ---- K3 trsm -----------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (64, 64), (65, 130), (150, 140), (512, 333), (1000, 1000)])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (64, 64), (65, 130), (128, 64), (150, 140), (200, 700), (256, 256), (257, 100),
+                                   (512, 333), (1000, 1000), (2048, 1500)])
 def test_trsm_matches_oracle(ctx, dtype, shape):
     k, nrhs = shape
     rng = np.random.default_rng([3, k, nrhs])
