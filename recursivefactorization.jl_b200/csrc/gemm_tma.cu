@@ -102,6 +102,18 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     __syncthreads();
 
+    // Pull this CTA's C tile into L2 while the main loop runs: the epilogue's read-modify-write then
+    // starts from L2 instead of paying an HBM round trip after the last MMA (matters for K <= 1024).
+    {
+        const int rr = (tid & 7) * 16;                 // 8 threads cover the 128 rows of a column (16 doubles = 128 B each)
+#pragma unroll
+        for (int c = tid >> 3; c < TBN; c += TTHREADS / 8) {
+            if (m0 + rr < M && n0 + c < N) {
+                const double *p = C + (m0 + rr) + (long long)(n0 + c) * lda;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        }
+    }
     const bool producer = (warp == 0 && lane == 0);
     auto produce = [&](int nk) {          // fill the ring slot of k-tile nk (one elected lane)
         const int s2 = nk % TSTAGES;

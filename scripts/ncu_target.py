@@ -17,6 +17,16 @@ if what == "lu":
     d.upload(a)
     d.lu()
     ctx.sync()
+elif what == "gemm32":
+    m, n, k = (int(x) for x in sys.argv[2:5])
+    lda = m + k
+    big = ctx.malloc(lda * (n + k) * 4)
+    ctx.memset(big, 0, lda * (n + k) * 4)
+    at = lambda r, c: C.c_void_p(big + (r + c * lda) * 4)
+    ctx.set_default_opts(f32_mode=1)
+    for _ in range(2):
+        ctx._check(ctx._lib.rfb_gemm_nn_sub_f32(ctx.handle, at(k, k), at(k, 0), at(0, k), m, n, k, lda))
+    ctx.sync()
 elif what == "gemm":
     m, n, k, path = (int(x) for x in sys.argv[2:6])
     lda = m + k
