@@ -10,7 +10,7 @@
 //   * the swizzle is matched by a permuted fragment map (which matrix row/column a DMMA fragment
 //     lane owns is free to choose), making every ld.shared.f64 of the inner loop conflict-free
 //     without padding -- padding is impossible with TMA's dense boxes;
-//   * tiles are rasterised in groups of 16 row-tiles so that a wave of 148 CTAs shares its A and B
+//   * tiles are rasterised in groups of 8 row-tiles so that a wave of 148 CTAs shares its A and B
 //     panels through the 126 MB L2.
 // Requirements: 16-byte aligned views and even lda (TMA global address / stride rules); anything
 // else goes to the generic cp.async kernel in gemm.cu.
@@ -32,7 +32,10 @@ constexpr int kStageABytes = TBM * TBK * 8;                    // 16 KB
 constexpr int kStageBBytes = TBN * TBK * 8;                    // 16 KB
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr size_t kTmaSmem = (size_t)TSTAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kGroupM = 16;
+// Rasterisation group: 8 row-tiles.  With K = 8192 one A row-tile panel is 8.4 MB, so a group's A panels
+// (67 MB) stay L2-resident while the CTAs sweep the column tiles; 16 row-tiles (134 MB > 126 MB L2) made
+// every wave re-read A from HBM (ncu: 19.1 GB read for 2.1 GB of operands, profiles/r01_gemm_f64_tma_*).
+constexpr int kGroupM = 8;
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 

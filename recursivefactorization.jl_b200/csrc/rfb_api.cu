@@ -27,6 +27,12 @@ struct LuPlan {
     int leaf;
     bool lists;            // K1 emits row-exchange lists and K2 consumes them (default)
     const rfb_opts *opts;
+    // early download (host mode): rows [0, n1) of the root are final long before the factorization ends
+    void *host_A = nullptr;            // caller's matrix (host), nullptr in device mode
+    int64_t host_lda = 0, host_m = 0;
+    int64_t early_rows = 0;            // rows [0, early_rows) of columns [0, early_cols) were already sent back
+    int64_t early_cols = 0;
+    bool is_root_call = true;          // cleared while recursing below the root node
     // pipelined upload (host mode): column chunk i is resident once up_events[i] has fired
     std::vector<cudaEvent_t> *up_events = nullptr;
     int64_t up_chunk = 0;  // columns per chunk
@@ -59,6 +65,8 @@ int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv,
 template <typename T>
 int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
            LuPlan &plan) {
+    const bool at_root = plan.is_root_call;
+    plan.is_root_call = false;
     T *A = root + c0 + c0 * lda;          // top-left of the node
     const int64_t mm = m - c0;            // rows of the node
     if (n <= plan.leaf) {                 // :192-195 leaf -> K1
@@ -71,6 +79,16 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
     RFB_TRY(need_cols(ctx, plan, c0 + n));
     RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));                          // :233
     RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
+    if (plan.host_A && at_root && n1 >= 1024) {
+        // root node, host mode: rows [0, n1) of ALL root columns (L11\U11 and U12) are final now -- the
+        // remaining steps only touch rows >= n1 -- so their download overlaps the trailing update.
+        RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
+        RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<T *>(plan.host_A), sizeof(T) * plan.host_lda, root, sizeof(T) * lda,
+                                        sizeof(T) * n1, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        plan.early_rows = n1;
+        plan.early_cols = n;
+    }
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan));               // :244
     return lu_swap<T>(ctx, A + n1, n1, lda, ipiv, c0 + n1, n2, plan);                   // :246
@@ -78,11 +96,15 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
 
 template <typename T>
 int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d_ipiv, int64_t *d_info,
-              const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, int64_t up_chunk = 0) {
+              const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, int64_t up_chunk = 0,
+              T *host_A = nullptr, int64_t host_lda = 0, int64_t *early_rows = nullptr, int64_t *early_cols = nullptr) {
     LuPlan plan;
     plan.opts = opts;
     plan.up_events = up_events;
     plan.up_chunk = up_chunk;
+    plan.host_A = host_A;
+    plan.host_lda = host_lda;
+    plan.host_m = m;
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
         return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
@@ -116,6 +138,8 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
         RFB_TRY(lu_swap<T>(ctx, AR, n - m, lda, d_ipiv, 0, mn, plan));
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
+    if (early_rows) *early_rows = plan.early_rows;
+    if (early_cols) *early_cols = plan.early_cols;
     return RFB_OK;
 }
 
@@ -216,10 +240,27 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
         RFB_CUDA(ctx, cudaEventRecord(ctx->up_events[c], ctx->copy_stream));
     }
     std::vector<cudaEvent_t> evs(ctx->up_events.begin(), ctx->up_events.begin() + nchunks);
-    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols));
+    int64_t early_rows = 0, early_cols = 0;
+    // the early download is only worth it (and only asynchronous) when the caller's matrix is page-locked
+    cudaPointerAttributes pattr;
+    const bool pinned = cudaPointerGetAttributes(&pattr, A) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols,
+                         (pinned && m >= n) ? A : nullptr, lda, &early_rows, &early_cols));
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
-    RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * lda, dA, sizeof(T) * ldd, sizeof(T) * m, n,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
+    // download what the early copy (rows [0, early_rows) of the first early_cols columns) did not cover
+    if (early_rows > 0) {
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(A + early_rows, sizeof(T) * lda, dA + early_rows, sizeof(T) * ldd,
+                                        sizeof(T) * (m - early_rows), early_cols, cudaMemcpyDeviceToHost, ctx->stream));
+        if (early_cols < n)
+            RFB_CUDA(ctx, cudaMemcpy2DAsync(A + early_cols * lda, sizeof(T) * lda, dA + early_cols * ldd, sizeof(T) * ldd,
+                                            sizeof(T) * m, n - early_cols, cudaMemcpyDeviceToHost, ctx->stream));
+        RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->copy_stream));
+        RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));    // the early copy must be done before we return
+    } else {
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * lda, dA, sizeof(T) * ldd, sizeof(T) * m, n,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+    }
     RFB_CUDA(ctx, cudaMemcpyAsync(ipiv, ctx->d_ipiv, sizeof(int64_t) * mn, cudaMemcpyDeviceToHost, ctx->stream));
     RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[0], ctx->d_info, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[1], &ctx->xchg->error_flag, sizeof(unsigned int),

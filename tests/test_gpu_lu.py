@@ -187,3 +187,18 @@ def test_baseline_config_f32_8192_tensor_core(ctx):
     assert np.all(np.abs(np.tril(F.factors, -1)) <= 1.0)
     res = hutchinson_residual(a0, F.factors, F.ipiv)
     assert res <= 20 * n * np.finfo(np.float32).eps, res
+
+
+def test_pinned_host_matrix_early_download(ctx):
+    """Page-locked caller matrix: the upload is pipelined and rows [0, n1) of the root are downloaded
+    while the trailing update still runs; the result must be identical to the pageable-path result."""
+    n = 4096
+    a0 = np.asfortranarray(np.random.default_rng(77).random((n, n)))
+    F_ref = rfb200.lu(a0, ctx=ctx)                       # pageable numpy memory
+    a_pin = ctx.pinned_empty((n, n), np.float64)
+    np.copyto(a_pin, a0)
+    ipiv = np.empty(n, dtype=np.int64)
+    F = rfb200.lu_(a_pin, ipiv, ctx=ctx)
+    assert F.info == 0
+    assert np.array_equal(F.ipiv, F_ref.ipiv)
+    assert np.array_equal(np.asarray(F.factors), F_ref.factors)
