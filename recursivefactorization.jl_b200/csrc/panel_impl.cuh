@@ -288,10 +288,29 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
     if (perm.width != nullptr && bid == 0 && tid == 0) perm.width[0] = n;
 }
 
+// How many CTAs of this instantiation can be co-resident (what a cooperative launch accepts).
+template <typename T, int NB, int THREADS>
+int panel_capacity(rfb_ctx *ctx) {
+    auto kern = panel_kernel<T, NB, THREADS>;
+    auto it = ctx->panel_capacity.find((const void *)kern);
+    if (it != ctx->panel_capacity.end()) return it->second;
+    constexpr size_t smem = sizeof(T) * NB * THREADS;
+    if (rfb_ensure_smem(ctx, (const void *)kern, smem) != RFB_OK) return 0;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    int cap = per_sm * ctx->sm_count;
+    if (cap > RFB_MAX_PANEL_CTAS) cap = RFB_MAX_PANEL_CTAS;
+    ctx->panel_capacity[(const void *)kern] = cap;
+    return cap;
+}
+
 template <typename T, int NB, int THREADS>
 int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
                       int64_t *info, int64_t col_offset, int G, PanelPermOut perm) {
     auto kern = panel_kernel<T, NB, THREADS>;
+    if (G > panel_capacity<T, NB, THREADS>(ctx))
+        return ctx->fail(RFB_ERR_UNSUPPORTED, "panel of %d rows x %d columns needs %d co-resident CTAs, the device holds %d", m, n, G,
+                         panel_capacity<T, NB, THREADS>(ctx));
     long long lda_ = lda, add_ = ipiv_add, off_ = col_offset;
     long long *ipiv_ = (long long *)ipiv, *info_ = (long long *)info;
     RfbPanelXchg *x = ctx->xchg;
@@ -336,19 +355,29 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
         RFB_CUDA(ctx, cudaMemsetAsync(ctx->xchg, 0, sizeof(RfbPanelXchg), ctx->stream));
         ctx->panel_epoch = 1;
     }
-    const int max_ctas = ctx->sm_count < RFB_MAX_PANEL_CTAS ? ctx->sm_count : RFB_MAX_PANEL_CTAS;
     int rc;
     const int64_t g128 = (m + 127) / 128, g256 = (m + 255) / 256;
     static const int force_threads = getenv("RFB_PANEL_THREADS") ? atoi(getenv("RFB_PANEL_THREADS")) : 0;   // tuning aid
-    if (g128 <= max_ctas && force_threads != 256)
+    // 128-thread CTAs spread over more SMs; the wide (64-column) kernel fits one 256-thread CTA per SM,
+    // which is what lets a 64-column panel reach 148 x 256 rows; narrower panels fit several CTAs per SM
+    int cap128 = n <= 16 ? panel_capacity<T, 16, 128>(ctx) : n <= 32 ? panel_capacity<T, 32, 128>(ctx) : panel_capacity<T, 64, 128>(ctx);
+    if (g128 <= cap128 && force_threads != 256)
         rc = launch_panel_threads<T, 128>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g128, perm);
-    else if (g256 <= max_ctas)
-        rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256, perm);
     else
-        return ctx->fail(RFB_ERR_UNSUPPORTED, "panel with %lld rows exceeds one-row-per-thread capacity (%d)",
-                         (long long)m, max_ctas * 256);
+        rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256, perm);
+    if (rc != RFB_OK) return rc;
     ctx->panel_epoch += (unsigned int)n;
     return rc;
 }
+
+template <typename T>
+int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m) {
+    const int64_t g128 = (m + 127) / 128, g256 = (m + 255) / 256;
+    if (g128 <= panel_capacity<T, 64, 128>(ctx) || g256 <= panel_capacity<T, 64, 256>(ctx)) return 64;
+    if (g128 <= panel_capacity<T, 32, 128>(ctx) || g256 <= panel_capacity<T, 32, 256>(ctx)) return 32;
+    if (g128 <= panel_capacity<T, 16, 128>(ctx) || g256 <= panel_capacity<T, 16, 256>(ctx)) return 16;
+    return 0;
+}
+template int rfb_panel_leaf_for_rows<RFB_PANEL_T>(rfb_ctx *, int64_t);
 
 template int rfb_launch_panel<RFB_PANEL_T>(rfb_ctx *, RFB_PANEL_T *, int64_t, int64_t, int64_t, int64_t *, int64_t, int64_t *, int64_t, int64_t);

@@ -108,6 +108,12 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
         return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
+    {   // very tall matrices: narrow the leaf until one row per thread fits the cooperative grid
+        const int fit = rfb_panel_leaf_for_rows<T>(ctx, m);
+        if (fit == 0)
+            return ctx->fail(RFB_ERR_UNSUPPORTED, "%lld rows exceed the panel kernel's one-row-per-thread capacity", (long long)m);
+        if (plan.leaf > fit) plan.leaf = fit;
+    }
     RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t), ctx->stream));
     const int64_t mn = m < n ? m : n;
     if (mn == 0) return RFB_OK;
@@ -156,6 +162,12 @@ int lu_range(rfb_ctx *ctx, T *A_root, int64_t m, int64_t lda, int64_t c0, int64_
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
         return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
+    {
+        const int fit = rfb_panel_leaf_for_rows<T>(ctx, m - c0);
+        if (fit == 0)
+            return ctx->fail(RFB_ERR_UNSUPPORTED, "%lld rows exceed the panel kernel's one-row-per-thread capacity", (long long)(m - c0));
+        if (plan.leaf > fit) plan.leaf = fit;
+    }
     plan.lists = !(opts && opts->laswp_path == 1);
     if (plan.lists && (ctx->perm_dst == nullptr || (size_t)(c0 + n) > ctx->perm_cap))
         return ctx->fail(RFB_ERR_ARG, "rfb_lu_range: exchange-list buffers missing or too small (rfb_perm_buffers)");

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <set>
+#include <map>
 
 #include "../../include/rfb200.h"
 
@@ -15,7 +16,7 @@
 // { epoch tag : 32 | payload : 32 } (the NCCL "LL" idea), so a reader never needs a fence and never
 // depends on 16-byte atomicity: it polls until the tags of all words it needs match the step.
 // ---------------------------------------------------------------------------------------------
-constexpr int RFB_MAX_PANEL_CTAS = 296;   // 148 SMs x 2
+constexpr int RFB_MAX_PANEL_CTAS = 768;   // 148 SMs x up to 5 co-resident CTAs of the narrow kernels
 constexpr int RFB_MAX_NB = 64;            // widest panel one launch factors
 
 struct alignas(128) RfbPanelHeader {   // one 128-byte line per CTA: 148 pollers do not pile up on one L2 line
@@ -71,6 +72,8 @@ struct rfb_ctx {
     std::vector<cudaEvent_t> prof_events; // pairs (start, stop) pending
     std::vector<int> prof_classes;
 
+    // co-resident CTA capacity of each panel-kernel instantiation (cooperative launch limit)
+    std::map<const void *, int> panel_capacity;
     // kernels whose dynamic shared memory limit has been raised on this device
     std::set<const void *> smem_configured;
 
@@ -131,6 +134,9 @@ struct RfbLaunchScope {
 template <typename T>
 int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
                      int64_t ipiv_add, int64_t *info_dev, int64_t col_offset, int64_t perm_row0 = -1);
+// widest leaf (64, 32 or 16 columns) whose one-row-per-thread cooperative grid can hold m rows; 0 = none
+template <typename T>
+int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m);
 // list-driven row interchange: applies the exchange lists of the panels covering pivots [k0, k1)
 // to the (rows >= k0) x ncols block whose first row is absolute row k0
 template <typename T>

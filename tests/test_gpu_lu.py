@@ -202,3 +202,16 @@ def test_pinned_host_matrix_early_download(ctx):
     assert F.info == 0
     assert np.array_equal(F.ipiv, F_ref.ipiv)
     assert np.array_equal(np.asarray(F.factors), F_ref.factors)
+
+
+@pytest.mark.parametrize("shape", [(50000, 48), (90000, 24), (40000, 200)])
+def test_very_tall_matrices_narrow_the_leaf(ctx, shape):
+    """More rows than one 64-column cooperative panel grid can hold (148 x 256): the driver narrows the
+    leaf to 32 / 16 columns (more co-resident CTAs) instead of failing; pivots still match LAPACK."""
+    m, n = shape
+    a0 = rand_matrix(np.random.default_rng([31, m, n]), m, n, np.float64)
+    F = rfb200.lu(a0, ctx=ctx)
+    _, piv, info = lapack.dgetrf(a0)
+    assert F.info == info == 0
+    assert np.array_equal(F.ipiv, piv + 1)
+    assert_testlu(a0, F.factors, F.ipiv, F.info, 0, wide=True)
