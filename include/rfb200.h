@@ -112,6 +112,19 @@ int rfb_gemm_nn_sub_f64(rfb_ctx *ctx, double *C, const double *A, const double *
 int rfb_gemm_nn_sub_f32(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m,
                         int64_t n, int64_t k, int64_t lda);
 int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);
+/* rfb_trsm_lunn: B (k x nrhs) <- U^-1 B with U the (non-unit) upper triangle of the k x k block at U:
+ * the back-substitution leg of `ldiv!(F::LU, B)` (LinearAlgebra; src/lu.jl:62 for the NotIPIV overload). */
+int rfb_trsm_lunn_f64(rfb_ctx *ctx, const double *U, int64_t k, double *B, int64_t nrhs, int64_t lda);
+int rfb_trsm_lunn_f32(rfb_ctx *ctx, const float *U, int64_t k, float *B, int64_t nrhs, int64_t lda);
+
+/* ---- consumer of the factorization: `ldiv!(F, B)` for a square LU --------
+ * B (n x nrhs) <- U^-1 L^-1 P B with the packed factors / pivots produced by rfb_lu_*.  Host mode copies
+ * factors, pivots and B in and B out; device mode works in place and needs ldb == lda (the kernels share
+ * one leading dimension).  A singular U (info > 0) gives Inf/NaN like LAPACK getrs, no error. */
+int rfb_solve_f64(rfb_ctx *ctx, const double *LU, int64_t n, int64_t lda, const int64_t *ipiv, double *B,
+                  int64_t nrhs, int64_t ldb, const rfb_opts *opts);
+int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const int64_t *ipiv, float *B,
+                  int64_t nrhs, int64_t ldb, const rfb_opts *opts);
 
 /* ---- building blocks of the multi-GPU driver (1-D block-cyclic columns) ----
  * The distributed recursion runs on the host (recursivefactorization.jl_b200/dist_lu.py, one process

@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import rfb_opts  # noqa: F401  (re-export)
 
 __all__ = [
-    "lu", "lu_", "LU", "SingularException", "RfbError", "Context", "default_context", "DeviceMatrix",
+    "lu", "lu_", "ldiv_", "LU", "SingularException", "RfbError", "Context", "default_context", "DeviceMatrix",
     "nsplit", "RowMaximum", "NoPivot",
 ]
 
@@ -272,6 +272,10 @@ class LU:
         out[np.arange(m), self.p] = 1
         return out
 
+    def solve(self, B: np.ndarray, ctx: Optional["Context"] = None) -> np.ndarray:
+        """``F \\ B``: returns ``U^-1 L^-1 P B`` computed on the GPU (does not modify ``B``)."""
+        return ldiv_(self, np.array(B, dtype=self.factors.dtype, order="F", copy=True), ctx=ctx)
+
     def __repr__(self):
         return f"LU(factors={self.factors.shape} {self.factors.dtype}, info={self.info})"
 
@@ -329,6 +333,31 @@ def lu_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, thread=Fal
     if check and info.value > 0:
         raise SingularException(info.value)
     return LU(A, ipiv, info.value)
+
+
+def ldiv_(F: LU, B: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
+    """``LinearAlgebra.ldiv!(F::LU, B)`` for a square factorization: overwrite ``B`` (vector or column-major
+    matrix of the factors' eltype) with ``U^-1 L^-1 P B`` (forward + back substitution on the GPU)."""
+    f = F.factors
+    n = f.shape[0]
+    if f.ndim != 2 or f.shape[1] != n:
+        raise ValueError("ldiv_ needs a square factorization")
+    if not isinstance(B, np.ndarray) or B.dtype != f.dtype or B.shape[0] != n or B.ndim not in (1, 2):
+        raise TypeError("B must be a numpy vector/matrix with n rows and the factors' eltype")
+    if not ((B.ndim == 1 and B.flags.c_contiguous) or (B.ndim == 2 and (B.flags.f_contiguous or B.shape[1] == 1))) \
+            or not B.flags.writeable:
+        raise TypeError("ldiv_ overwrites B and needs a writeable column-major array")
+    if not f.flags.f_contiguous:
+        f = np.asfortranarray(f)
+    nrhs = 1 if B.ndim == 1 else B.shape[1]
+    ipiv = np.ascontiguousarray(F.ipiv, dtype=np.int64)
+    ctx = ctx or default_context()
+    lib = ctx._lib
+    fn = lib.rfb_solve_f64 if f.dtype == np.float64 else lib.rfb_solve_f32
+    opts = _make_opts(_lib.RFB_MEM_HOST)
+    ctx._check(fn(ctx.handle, C.c_void_p(f.ctypes.data), n, max(n, 1), C.c_void_p(ipiv.ctypes.data),
+                  C.c_void_p(B.ctypes.data), nrhs, max(n, 1), C.byref(opts)))
+    return B
 
 
 def lu(A, pivot=True, thread=False, **kwargs) -> LU:

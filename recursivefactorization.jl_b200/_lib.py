@@ -55,6 +55,10 @@ SIGNATURES = {
     "rfb_gemm_nn_sub_f64": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64]),
     "rfb_gemm_nn_sub_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64]),
     "rfb_ipiv_shift": (_int, [_p, _p, _i64, _i64]),
+    "rfb_trsm_lunn_f64": (_int, [_p, _p, _i64, _p, _i64, _i64]),
+    "rfb_trsm_lunn_f32": (_int, [_p, _p, _i64, _p, _i64, _i64]),
+    "rfb_solve_f64": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, C.POINTER(rfb_opts)]),
+    "rfb_solve_f32": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, C.POINTER(rfb_opts)]),
     "rfb_lu_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_range_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_laswp_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),

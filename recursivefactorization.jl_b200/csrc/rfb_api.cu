@@ -189,6 +189,58 @@ int laswp_range(rfb_ctx *ctx, T *A_root, int64_t lda, int64_t col0, int64_t ncol
     return rfb_launch_laswp<T>(ctx, A, ncols, lda, ipiv + k0, k1 - k0, k0);
 }
 
+// ldiv!(F::LU, B): B <- U^-1 L^-1 P B
+template <typename T>
+int solve_entry(rfb_ctx *ctx, const T *LU, int64_t n, int64_t lda, const int64_t *ipiv, T *B, int64_t nrhs, int64_t ldb,
+                const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (n < 0 || nrhs < 0) return ctx->fail(RFB_ERR_ARG, "negative dimension");
+    if (n == 0 || nrhs == 0) return RFB_OK;
+    if (!LU || !ipiv || !B) return ctx->fail(RFB_ERR_ARG, "null pointer");
+    if (lda < n || ldb < n) return ctx->fail(RFB_ERR_ARG, "leading dimension smaller than n");
+    RFB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int space = opts ? opts->mem_space : RFB_MEM_HOST;
+    if (space == RFB_MEM_DEVICE) {
+        if (ldb != lda) return ctx->fail(RFB_ERR_UNSUPPORTED, "device-mode solve needs ldb == lda (one shared leading dimension)");
+        RFB_TRY(rfb_launch_laswp<T>(ctx, B, nrhs, ldb, ipiv, n, 0));
+        RFB_TRY(rfb_launch_trsm<T>(ctx, LU, n, B, nrhs, lda, opts));
+        return rfb_launch_trsm_upper<T>(ctx, LU, n, B, nrhs, lda, opts);
+    }
+    const int64_t ldd = (n + 3) & ~int64_t(3);
+    const size_t need = sizeof(T) * (size_t)ldd * (size_t)(n + nrhs);
+    if (need > ctx->d_mat_cap) {
+        if (ctx->d_mat) cudaFree(ctx->d_mat);
+        ctx->d_mat = nullptr;
+        ctx->d_mat_cap = 0;
+        if (cudaMalloc(&ctx->d_mat, need) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the solve", need);
+        }
+        ctx->d_mat_cap = need;
+    }
+    if ((size_t)n > ctx->d_ipiv_cap) {
+        if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
+        ctx->d_ipiv = nullptr;
+        ctx->d_ipiv_cap = 0;
+        if (cudaMalloc(&ctx->d_ipiv, sizeof(int64_t) * (size_t)n) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate the device pivot vector");
+        }
+        ctx->d_ipiv_cap = (size_t)n;
+    }
+    T *dLU = reinterpret_cast<T *>(ctx->d_mat);
+    T *dB = dLU + (size_t)ldd * n;
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(dLU, sizeof(T) * ldd, LU, sizeof(T) * lda, sizeof(T) * n, n, cudaMemcpyHostToDevice, ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(dB, sizeof(T) * ldd, B, sizeof(T) * ldb, sizeof(T) * n, nrhs, cudaMemcpyHostToDevice, ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ipiv, ipiv, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    RFB_TRY(rfb_launch_laswp<T>(ctx, dB, nrhs, ldd, ctx->d_ipiv, n, 0));
+    RFB_TRY(rfb_launch_trsm<T>(ctx, dLU, n, dB, nrhs, ldd, opts));
+    RFB_TRY(rfb_launch_trsm_upper<T>(ctx, dLU, n, dB, nrhs, ldd, opts));
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(B, sizeof(T) * ldb, dB, sizeof(T) * ldd, sizeof(T) * n, nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RFB_OK;
+}
+
 template <typename T>
 int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
              const rfb_opts *opts) {
@@ -477,6 +529,22 @@ int rfb_gemm_nn_sub_f32(rfb_ctx *ctx, float *C, const float *A, const float *B, 
                         int64_t lda) {
     RFB_CHECK_CTX(ctx);
     return rfb_launch_gemm<float>(ctx, C, A, B, m, n, k, lda, &ctx->default_opts);
+}
+int rfb_trsm_lunn_f64(rfb_ctx *ctx, const double *U, int64_t k, double *B, int64_t nrhs, int64_t lda) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_trsm_upper<double>(ctx, U, k, B, nrhs, lda, &ctx->default_opts);
+}
+int rfb_trsm_lunn_f32(rfb_ctx *ctx, const float *U, int64_t k, float *B, int64_t nrhs, int64_t lda) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_trsm_upper<float>(ctx, U, k, B, nrhs, lda, &ctx->default_opts);
+}
+int rfb_solve_f64(rfb_ctx *ctx, const double *LU, int64_t n, int64_t lda, const int64_t *ipiv, double *B, int64_t nrhs,
+                  int64_t ldb, const rfb_opts *opts) {
+    return solve_entry<double>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts);
+}
+int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const int64_t *ipiv, float *B, int64_t nrhs,
+                  int64_t ldb, const rfb_opts *opts) {
+    return solve_entry<float>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts);
 }
 int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift) {
     RFB_CHECK_CTX(ctx);

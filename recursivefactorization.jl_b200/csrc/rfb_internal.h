@@ -148,6 +148,8 @@ template <typename T>
 int rfb_launch_trsm(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t lda,
                     const rfb_opts *opts);
 template <typename T>
+int rfb_launch_trsm_upper(rfb_ctx *ctx, const T *U, int64_t k, T *B, int64_t nrhs, int64_t lda, const rfb_opts *opts);
+template <typename T>
 int rfb_launch_gemm(rfb_ctx *ctx, T *C, const T *A, const T *B, int64_t m, int64_t n, int64_t k,
                     int64_t lda, const rfb_opts *opts);
 int rfb_launch_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);

@@ -165,6 +165,119 @@ int launch_block(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t l
     return RFB_OK;
 }
 
+// Upper-triangular, non-unit twin of trsm_block_kernel for the back substitution of an LU solve
+// (`ldiv!(UpperTriangular(F.factors), B)`, src/lu.jl:62): sub-blocks and 8-row phases run bottom-up,
+// the owning warp divides by the diagonal.  Padding rows of a ragged last sub-block get a unit diagonal.
+template <typename T>
+__global__ void __launch_bounds__(kBlkThreads)
+trsm_upper_block_kernel(const T *__restrict__ U, int kb, T *__restrict__ B, long long nrhs, long long lda) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sL = reinterpret_cast<T *>(smem_raw);                    // [64 cols][64 rows] of the current U block
+    T *sX = sL + kSub * kSub;                                   // [4 sub-blocks][64 rows][32 cols]
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const long long col = (long long)blockIdx.x * kBlkCols + lane;
+    const bool active = col < nrhs;
+    T *xcol = B + (active ? col : 0) * lda;
+    const int nsub = (kb + kSub - 1) / kSub;
+
+    T tl[16];
+    auto fetch = [&](int s, int t) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + kBlkThreads * i, r = e & 63, c = e >> 6;
+            const int gr = s * kSub + r, gc = t * kSub + c;
+            T v = (gr < kb && gc < kb) ? U[gr + (long long)gc * lda] : T(0);
+            if (gr == gc && gr >= kb) v = T(1);
+            tl[i] = v;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = tid + kBlkThreads * i;
+            sL[(e >> 6) * kSub + (e & 63)] = tl[i];
+        }
+    };
+
+    fetch(nsub - 1, nsub - 1);
+    for (int s = nsub - 1; s >= 0; --s) {
+        const int r0 = s * kSub + 8 * g;
+        T x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = (active && r0 + q < kb) ? xcol[r0 + q] : T(0);
+        for (int t = nsub - 1; t >= s; --t) {
+            __syncthreads();
+            stash();
+            if (t > s) fetch(s, t - 1);
+            else if (s > 0) fetch(s - 1, nsub - 1);
+            __syncthreads();
+            if (t > s) {                              // x_s -= U_st x_t
+                const T *xt = sX + t * kSub * kBlkCols + lane;
+#pragma unroll 8
+                for (int j = 0; j < kSub; ++j) {
+                    const T nv = -xt[j * kBlkCols];
+                    const T *lj = sL + j * kSub + 8 * g;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = fma(lj[q], nv, x[q]);
+                }
+            } else {                                  // diagonal 64 x 64 upper triangle, bottom-up phases
+                T *xs = sX + s * kSub * kBlkCols + lane;
+#pragma unroll 1
+                for (int p = 7; p >= 0; --p) {
+                    if (g == p) {
+#pragma unroll
+                        for (int c = 7; c >= 0; --c) {
+                            const T *lc = sL + (8 * p + c) * kSub + 8 * p;
+                            x[c] = x[c] / lc[c];
+                            const T nxc = -x[c];
+#pragma unroll
+                            for (int q = 0; q < c; ++q) x[q] = fma(lc[q], nxc, x[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) xs[(8 * p + q) * kBlkCols] = x[q];
+                    }
+                    __syncthreads();
+                    if (g < p) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const T nv = -xs[(8 * p + c) * kBlkCols];
+                            const T *lc = sL + (8 * p + c) * kSub + 8 * g;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) x[q] = fma(lc[q], nv, x[q]);
+                        }
+                    }
+                }
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (r0 + q < kb) xcol[r0 + q] = x[q];
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+int launch_upper_block(rfb_ctx *ctx, const T *U, int kb, T *B, int64_t nrhs, int64_t lda) {
+    constexpr size_t smem = sizeof(T) * (kSub * kSub + 4 * kSub * kBlkCols);
+    auto kern = trsm_upper_block_kernel<T>;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
+    RfbLaunchScope scope(ctx, RFB_KC_TRSM, (double)kb * (double)kb * (double)nrhs);
+    kern<<<(unsigned int)((nrhs + kBlkCols - 1) / kBlkCols), kBlkThreads, smem, ctx->stream>>>(U, kb, B, nrhs, lda);
+    RFB_CUDA(ctx, cudaGetLastError());
+    return RFB_OK;
+}
+
+template <typename T>
+int trsm_upper_rec(rfb_ctx *ctx, const T *U, int64_t k, T *B, int64_t nrhs, int64_t lda, const rfb_opts *opts) {
+    if (k <= 256) return launch_upper_block<T>(ctx, U, (int)k, B, nrhs, lda);
+    int64_t k1 = ((k / 2 + 255) / 256) * 256;
+    if (k1 >= k) k1 = ((k - 1) / 256) * 256;
+    RFB_TRY(trsm_upper_rec<T>(ctx, U + k1 + k1 * lda, k - k1, B + k1, nrhs, lda, opts));        // bottom block first
+    RFB_TRY(rfb_launch_gemm<T>(ctx, B, U + k1 * lda, B + k1, k1, nrhs, k - k1, lda, opts));      // B1 -= U12 X2
+    return trsm_upper_rec<T>(ctx, U, k1, B, nrhs, lda, opts);
+}
+
 template <typename T, int TB>
 int launch_diag(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
     constexpr int COLS = TB;
@@ -206,3 +319,11 @@ int rfb_launch_trsm(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int
 
 template int rfb_launch_trsm<double>(rfb_ctx *, const double *, int64_t, double *, int64_t, int64_t, const rfb_opts *);
 template int rfb_launch_trsm<float>(rfb_ctx *, const float *, int64_t, float *, int64_t, int64_t, const rfb_opts *);
+
+template <typename T>
+int rfb_launch_trsm_upper(rfb_ctx *ctx, const T *U, int64_t k, T *B, int64_t nrhs, int64_t lda, const rfb_opts *opts) {
+    if (k <= 0 || nrhs <= 0) return RFB_OK;
+    return trsm_upper_rec<T>(ctx, U, k, B, nrhs, lda, opts);
+}
+template int rfb_launch_trsm_upper<double>(rfb_ctx *, const double *, int64_t, double *, int64_t, int64_t, const rfb_opts *);
+template int rfb_launch_trsm_upper<float>(rfb_ctx *, const float *, int64_t, float *, int64_t, int64_t, const rfb_opts *);

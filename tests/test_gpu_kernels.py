@@ -227,3 +227,28 @@ def test_gemm_f32_tcgen05_matches_oracle(ctx, shape):
     untouched[c_off[0]:c_off[0] + m, c_off[1]:c_off[1] + n] = False
     assert np.array_equal(got[untouched], big[untouched])
     d.free()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (64, 64), (65, 130), (200, 700), (256, 256), (257, 100), (1000, 300), (2048, 1500)])
+def test_trsm_upper_matches_numpy(ctx, dtype, shape):
+    """Back-substitution kernel (non-unit upper) against a float64 triangular solve."""
+    import scipy.linalg as sl
+    k, nrhs = shape
+    rng = np.random.default_rng([33, k, nrhs])
+    big = rand_matrix(rng, k + 5, k + nrhs + 3, dtype)
+    u = np.triu(big[2:2 + k, 1:1 + k]).astype(np.float64)
+    u[np.arange(k), np.arange(k)] += 2.0                       # well-conditioned diagonal
+    big[2:2 + k, 1:1 + k] = np.where(np.triu(np.ones((k, k), dtype=bool)), u, big[2:2 + k, 1:1 + k]).astype(dtype)
+    if k > 16:
+        big[2:2 + k, 1:1 + k] = np.where(np.triu(np.ones((k, k), dtype=bool), 1), big[2:2 + k, 1:1 + k] * dtype(2.0 / k), big[2:2 + k, 1:1 + k])
+    uu = np.triu(big[2:2 + k, 1:1 + k].astype(np.float64))
+    want = sl.solve_triangular(uu, big[2:2 + k, k + 2:k + 2 + nrhs].astype(np.float64), lower=False)
+    d = Dev(ctx, big)
+    ctx._check(fn(ctx, "rfb_trsm_lunn", dtype)(ctx.handle, d.at(2, 1), k, d.at(2, k + 2), nrhs, d.lda))
+    got = d.get()
+    tol = 50 * max(k, 8) * float(np.finfo(dtype).eps) * max(1.0, float(np.abs(want).max()))
+    assert np.abs(got[2:2 + k, k + 2:k + 2 + nrhs] - want).max() <= tol
+    mask = np.ones_like(big, dtype=bool); mask[2:2 + k, k + 2:k + 2 + nrhs] = False
+    assert np.array_equal(got[mask], big[mask])
+    d.free()

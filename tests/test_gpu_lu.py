@@ -215,3 +215,22 @@ def test_very_tall_matrices_narrow_the_leaf(ctx, shape):
     assert F.info == info == 0
     assert np.array_equal(F.ipiv, piv + 1)
     assert_testlu(a0, F.factors, F.ipiv, F.info, 0, wide=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (9, 1), (64, 3), (130, 1), (300, 7), (1000, 33), (2500, 512)])
+def test_ldiv_solve(ctx, dtype, n, nrhs):
+    """`ldiv!(F, B)` on the GPU (forward + back substitution with the K3 kernels): the solve check of
+    test/runtests.jl:21-28 (`ldiv!(MF, A[:, end]) == e_n`, atol 100 E) and A X = B residuals."""
+    rng = np.random.default_rng([9, n, nrhs])
+    a0 = rand_matrix(rng, n, n, dtype)
+    F = rfb200.lu(a0, ctx=ctx)
+    eps = float(np.finfo(dtype).eps)
+    x = F.solve(a0[:, -1].copy(), ctx=ctx)
+    rhs = np.zeros(n); rhs[-1] = 1
+    assert np.allclose(x, rhs, rtol=0, atol=100 * 20 * n * eps * max(1.0, np.linalg.cond(a0.astype(np.float64)) * eps * 10))
+    b = np.asfortranarray(rng.random((n, nrhs), dtype=dtype))
+    xs = rfb200.ldiv_(F, b.copy(order="F"), ctx=ctx)
+    xw = np.linalg.solve(a0.astype(np.float64), b.astype(np.float64))
+    r = np.abs(a0.astype(np.float64) @ xs.astype(np.float64) - b.astype(np.float64)).max()
+    assert r <= 1000 * n * eps * max(1.0, np.abs(xw).max()), r        # the reference's solve bound (runtests.jl:82)
