@@ -109,6 +109,20 @@ for (f, W) in ((:adjoint, :Adjoint), (:transpose, :Transpose)), g in (:lu, :lu!)
     @eval $g(A::$W, args...; kwargs...) = $f($g(parent(A), args...; kwargs...))
 end
 
+# ldiv!(F, B) on the GPU for factorizations produced above (square, Float64): forward + back substitution
+function ldiv_gpu!(F::LU{Float64, <:StridedMatrix{Float64}, <:Vector{BlasInt}}, B::StridedVecOrMat{Float64};
+        ctx::Context = default_context())
+    n = size(F.factors, 1)
+    size(F.factors, 2) == n && size(B, 1) == n || throw(DimensionMismatch("square LU and n-row right-hand side expected"))
+    o = Ref(RfbOpts())
+    rc = GC.@preserve F B ccall((:rfb_solve_f64, librfb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Ptr{RfbOpts}),
+        ctx.handle, pointer(F.factors), n, stride(F.factors, 2), pointer(F.ipiv), pointer(B), size(B, 2),
+        B isa AbstractVector ? n : stride(B, 2), o)
+    rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+    return B
+end
+
 # everything else is not on the GPU path: fail loudly instead of silently running on the CPU
 lu!(A::AbstractMatrix, args...; kwargs...) =
     throw(ArgumentError("rfb200 supports strided Float64/Float32 matrices only, got $(typeof(A))"))
