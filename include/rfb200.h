@@ -60,7 +60,10 @@ typedef struct rfb_opts {
     int32_t trsm_block;  /* 0 = default; diagonal block of the blocked TRSM                   */
     int32_t gemm_path;   /* 0 = auto, 1 = force generic (cp.async) tiles, 2 = force TMA tiles */
     int32_t laswp_path;  /* 0 = auto, 1 = force the ipiv-driven kernel                        */
-    int32_t reserved[10];
+    int32_t no_pivot;    /* 1 = pivot = Val(false) / NoPivot() (src/lu.jl:27-65): no row interchanges,
+                            `ipiv` may be NULL (NotIPIV) or is filled with 1:min(m,n) (:107-113), a
+                            zero pivot is reported as NEGATIVE info (Julia >= 1.11, :24-25, :323-326) */
+    int32_t reserved[9];
 } rfb_opts;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -121,10 +124,52 @@ int rfb_trsm_lunn_f32(rfb_ctx *ctx, const float *U, int64_t k, float *B, int64_t
  * B (n x nrhs) <- U^-1 L^-1 P B with the packed factors / pivots produced by rfb_lu_*.  Host mode copies
  * factors, pivots and B in and B out; device mode works in place and needs ldb == lda (the kernels share
  * one leading dimension).  A singular U (info > 0) gives Inf/NaN like LAPACK getrs, no error. */
+/* ipiv == NULL: the factorization is unpivoted (NotIPIV), no row interchanges are applied. */
 int rfb_solve_f64(rfb_ctx *ctx, const double *LU, int64_t n, int64_t lda, const int64_t *ipiv, double *B,
                   int64_t nrhs, int64_t ldb, const rfb_opts *opts);
 int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const int64_t *ipiv, float *B,
                   int64_t nrhs, int64_t ldb, const rfb_opts *opts);
+
+/* ---- pivot = Val(false) and the butterfly solver ---------------------------
+ * The NoPivot factorization itself is rfb_lu_* with opts->no_pivot = 1; rfb_solve_* with ipiv == NULL is
+ * `ldiv!(F::LU{..,NotIPIV}, B)` (src/lu.jl:60-64).
+ * rfb_panel_getrf_nopiv: src/lu.jl:290-338 with Pivot = false on an m x n device panel (n <= 64, m >= n);
+ *   a zero pivot at local column k sets *info_dev = -(col_offset + k + 1) if it was 0.
+ * rfb_butterfly_mul: `🦋mul!(A, uv)` (src/butterflylu.jl:93-113): the n x n device matrix (n % 4 == 0)
+ *   becomes U' A V for the two-level random butterflies held in uv_dev (4 n values laid out as the
+ *   reference's `uv`: U1 | V1 | U2 | V2 | U | V with lengths n/2, n/2, n/2, n/2, n, n).
+ * rfb_butterfly_vec: which = 0: B <- U' B (src/butterflylu.jl:50); which = 1: B <- V B (:52); B is n x nrhs.
+ * rfb_butterfly_solve: the whole `🦋solve!` (src/butterflylu.jl:45-55) for A x = b.  Host mode: A (n x n,
+ *   NOT modified), B (n x nrhs, overwritten with the solution) and uv (4 * npad values, npad = n rounded up
+ *   to a multiple of 4 -- the library pads like `pad!`, :180-197) are host pointers.  Device mode: in place
+ *   on device buffers, n % 4 == 0, ldb == lda; A is overwritten with the factors of U' A V.
+ *   *info is the NoPivot factorization's info (0, or -k for a zero pivot at column k). */
+int rfb_panel_getrf_nopiv_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev,
+                              int64_t col_offset);
+int rfb_panel_getrf_nopiv_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev,
+                              int64_t col_offset);
+int rfb_butterfly_mul_f64(rfb_ctx *ctx, double *A, int64_t n, int64_t lda, const double *uv_dev);
+int rfb_butterfly_mul_f32(rfb_ctx *ctx, float *A, int64_t n, int64_t lda, const float *uv_dev);
+int rfb_butterfly_vec_f64(rfb_ctx *ctx, double *B, int64_t n, int64_t nrhs, int64_t ldb, const double *uv_dev,
+                          int which);
+int rfb_butterfly_vec_f32(rfb_ctx *ctx, float *B, int64_t n, int64_t nrhs, int64_t ldb, const float *uv_dev,
+                          int which);
+int rfb_butterfly_solve_f64(rfb_ctx *ctx, const double *A, int64_t n, int64_t lda, double *B, int64_t nrhs,
+                            int64_t ldb, const double *uv, int64_t *info, const rfb_opts *opts);
+int rfb_butterfly_solve_f32(rfb_ctx *ctx, const float *A, int64_t n, int64_t lda, float *B, int64_t nrhs,
+                            int64_t ldb, const float *uv, int64_t *info, const rfb_opts *opts);
+
+/* ---- batched factorization -------------------------------------------------
+ * `lu!` on each of `batch` m x n matrices A + b * stride_a (column-major, shared lda): ipiv holds
+ * batch * min(m, n) pivots (matrix b at offset b * min(m, n), 1-based, local to its matrix), info holds
+ * batch words.  The reference has no batched call; its motivating workload is (README.md:34-35, many small
+ * Jacobians), and each matrix gets exactly what `lu!` gives it.  Small pivoted matrices (n <= 64, m <= 128)
+ * are factored by one launch with one CTA per matrix running the unblocked loop the reference uses below
+ * its threshold (src/lu.jl:125-126, :290-338); larger ones run the recursive driver one after another. */
+int rfb_lu_batched_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                       int64_t *ipiv, int64_t *info, const rfb_opts *opts);
+int rfb_lu_batched_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                       int64_t *ipiv, int64_t *info, const rfb_opts *opts);
 
 /* ---- building blocks of the multi-GPU driver (1-D block-cyclic columns) ----
  * The distributed recursion runs on the host (recursivefactorization.jl_b200/dist_lu.py, one process

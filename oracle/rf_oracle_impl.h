@@ -13,25 +13,29 @@
  * explicit fma() makes the oracle's bits independent of the host it runs on.
  */
 
-/* ---- src/lu.jl:290-338  _generic_lufact!(A, Val(true), ipiv, info) -------------------------
+/* ---- src/lu.jl:290-338  _generic_lufact!(A, Val(Pivot), ipiv, info) ------------------------
  * Unblocked right-looking LU of the m x n block A with npiv = length(ipiv) pivot steps.
+ * pivot == 0 is Val(false): kp = k, ipiv is not touched (NotIPIV, :27-32), and a zero pivot is
+ * reported as NEGATIVE info (the Julia >= 1.11 convention, :24-25 and :323-326).
  * pivot = FIRST index of the strict maximum |A[i,k]| starting from amax = 0 (:296-305);
  * swap rows k,kp over all n columns of the block (:308-315); scale by the RECIPROCAL
  * (:317-320); info = first k with an exactly-zero pivot, factorization continues (:321-327);
  * rank-1 update of the remaining columns (:330-334).  ipiv is 1-based and block-local. */
 RFO_CLONES
 static int64_t RFO_(rfo_generic_lufact)(RFO_T *A, int64_t m, int64_t n, int64_t lda,
-                                        int64_t *ipiv, int64_t npiv, int64_t info)
+                                        int64_t *ipiv, int64_t npiv, int64_t info, int pivot)
 {
     for (int64_t k = 0; k < npiv; ++k) {
         RFO_T *ck = A + k * lda;
         int64_t kp = k;
-        RFO_T amax = (RFO_T)0;
-        for (int64_t i = k; i < m; ++i) {
-            RFO_T absi = ck[i] < 0 ? -ck[i] : ck[i];
-            if (absi > amax) { kp = i; amax = absi; }   /* NaN never wins: (NaN > x) is false */
+        if (pivot) {
+            RFO_T amax = (RFO_T)0;
+            for (int64_t i = k; i < m; ++i) {
+                RFO_T absi = ck[i] < 0 ? -ck[i] : ck[i];
+                if (absi > amax) { kp = i; amax = absi; }   /* NaN never wins: (NaN > x) is false */
+            }
+            ipiv[k] = kp + 1;
         }
-        ipiv[k] = kp + 1;
         if (ck[kp] != (RFO_T)0) {                        /* !iszero: NaN counts as non-zero */
             if (k != kp) {
                 for (int64_t j = 0; j < n; ++j) {
@@ -43,7 +47,7 @@ static int64_t RFO_(rfo_generic_lufact)(RFO_T *A, int64_t m, int64_t n, int64_t 
             RFO_T inv = (RFO_T)1 / ck[k];
             for (int64_t i = k + 1; i < m; ++i) ck[i] *= inv;
         } else if (info == 0) {
-            info = k + 1;
+            info = pivot ? k + 1 : -(k + 1);             /* :321-327 */
         }
         if (k == npiv - 1) break;
         for (int64_t j = k + 1; j < n; ++j) {
@@ -168,24 +172,26 @@ static int64_t RFO_(rfo_nsplit)(int64_t n)
     return n >= k ? ((n + k2) / k) * k2 : n / 2;
 }
 
-/* ---- src/lu.jl:189-263  reckernel!(A, Val(true), m, n, ipiv, info, blocksize, thread) -------*/
+/* ---- src/lu.jl:189-263  reckernel!(A, Val(Pivot), m, n, ipiv, info, blocksize, thread) ------
+ * pivot == 0: no row interchanges (:233, :246 are guarded by `Pivot &&`), ipiv untouched,
+ * negative info shifted by -n1 (:249-251). */
 static int64_t RFO_(rfo_reckernel)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
-                                   int64_t info, int64_t blocksize, int threads)
+                                   int64_t info, int64_t blocksize, int threads, int pivot)
 {
     if (n <= (blocksize > 1 ? blocksize : 1))                                   /* :192-195 */
-        return RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, n, info);
+        return RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, n, info, pivot);
     int64_t n1 = RFO_(rfo_nsplit)(n), n2 = n - n1, m2 = m - n1;                 /* :196-198 */
     RFO_T *AR = A + n1 * lda, *A21 = A + n1, *A22 = A + n1 + n1 * lda;          /* :210-218 */
     int64_t *P1 = ipiv, *P2 = ipiv + n1;                                        /* :221-222 */
-    info = RFO_(rfo_reckernel)(A, m, n1, lda, P1, info, blocksize, threads);    /* :229 */
-    RFO_(rfo_apply_permutation)(P1, n1, AR, n2, lda, threads);                  /* :233 */
+    info = RFO_(rfo_reckernel)(A, m, n1, lda, P1, info, blocksize, threads, pivot); /* :229 */
+    if (pivot) RFO_(rfo_apply_permutation)(P1, n1, AR, n2, lda, threads);       /* :233 */
     RFO_(rfo_trsm_llnu)(A, n1, AR, n2, lda, threads);                           /* :235 */
     RFO_(rfo_schur_complement)(A22, A21, AR, m2, n2, n1, lda, threads);         /* :240 */
     int64_t previnfo = info;                                                    /* :242 */
-    info = RFO_(rfo_reckernel)(A22, m2, n2, lda, P2, info, blocksize, threads); /* :244 */
-    RFO_(rfo_apply_permutation)(P2, n2, A21, n1, lda, threads);                 /* :246 */
-    if (info != previnfo) info += n1;                                           /* :248-255 */
-    for (int64_t i = 0; i < n2; ++i) P2[i] += n1;                               /* :256-260 */
+    info = RFO_(rfo_reckernel)(A22, m2, n2, lda, P2, info, blocksize, threads, pivot); /* :244 */
+    if (pivot) RFO_(rfo_apply_permutation)(P2, n2, A21, n1, lda, threads);      /* :246 */
+    if (info != previnfo) info += (info < 0) ? -n1 : n1;                        /* :248-255 */
+    if (pivot) for (int64_t i = 0; i < n2; ++i) P2[i] += n1;                    /* :256-260 */
     return info;
 }
 
@@ -193,31 +199,101 @@ static int64_t RFO_(rfo_reckernel)(RFO_T *A, int64_t m, int64_t n, int64_t lda, 
  * blocksize <= 0 selects the reference default (length(A) >= 40000 ? 8 : 16, :101);
  * threshold <= 0 selects pick_threshold() for a 64-byte SIMD register, i.e. 48 (:90,:102).
  * Returns info; never throws (checknonsingular, :128, is the caller's job). */
-int64_t RFO_(rfo_lu)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
-                     int64_t blocksize, int64_t threshold, int threads)
+static int64_t RFO_(rfo_lu_impl)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+                                 int64_t blocksize, int64_t threshold, int threads, int pivot)
 {
     if (blocksize <= 0) blocksize = (m * n >= 40000) ? 8 : 16;
     if (threshold <= 0) threshold = 48;
     if (threads < 1) threads = 1;
     int64_t mn = m < n ? m : n, info = 0;
     if (mn == 0) return 0;
+    if (!pivot && ipiv) for (int64_t i = 0; i < mn; ++i) ipiv[i] = i + 1;       /* :111-113 */
     if (mn > threshold) {                                                       /* :114 */
-        info = RFO_(rfo_reckernel)(A, m, mn, lda, ipiv, info, blocksize, threads); /* :147 */
+        info = RFO_(rfo_reckernel)(A, m, mn, lda, ipiv, info, blocksize, threads, pivot); /* :147 */
         if (m < n) {                                                            /* :148-154 */
             RFO_T *AR = A + m * lda;
-            RFO_(rfo_apply_permutation)(ipiv, mn, AR, n - m, lda, threads);
+            if (pivot) RFO_(rfo_apply_permutation)(ipiv, mn, AR, n - m, lda, threads);
             RFO_(rfo_trsm_llnu)(A, m, AR, n - m, lda, threads);
         }
     } else {
-        info = RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, mn, info);          /* :125-126 */
+        info = RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, mn, info, pivot);   /* :125-126 */
     }
     return info;
+}
+int64_t RFO_(rfo_lu)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+                     int64_t blocksize, int64_t threshold, int threads)
+{ return RFO_(rfo_lu_impl)(A, m, n, lda, ipiv, blocksize, threshold, threads, 1); }
+/* lu!(A, ipiv, Val(false), thread): ipiv may be NULL (NotIPIV) or a user vector that is filled
+ * with 1:min(m,n) (:107-113). */
+int64_t RFO_(rfo_lu_nopiv)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv,
+                           int64_t blocksize, int64_t threshold, int threads)
+{ return RFO_(rfo_lu_impl)(A, m, n, lda, ipiv, blocksize, threshold, threads, 0); }
+
+/* ---- src/lu.jl:60-64  ldiv!(F::LU{T,<:StridedMatrix,<:NotIPIV}, B) ---------------------------
+ * B <- U^-1 (L^-1 B) with the packed factors; both legs are TriangularSolve.ldiv! calls (an
+ * un-vendored dependency, see rfo_trsm_llnu): forward substitution with the unit lower triangle,
+ * then column-oriented back substitution with the upper triangle (division by the diagonal). */
+void RFO_(rfo_ldiv_notipiv)(const RFO_T *F, int64_t n, int64_t lda, RFO_T *B, int64_t nrhs, int64_t ldb)
+{
+    for (int64_t j = 0; j < nrhs; ++j) {
+        RFO_T *x = B + j * ldb;
+        for (int64_t c = 0; c < n; ++c) {
+            const RFO_T *l = F + c * lda;
+            RFO_T xc = x[c];
+            for (int64_t r = c + 1; r < n; ++r) x[r] = RFO_FMA(-l[r], xc, x[r]);
+        }
+        for (int64_t c = n - 1; c >= 0; --c) {
+            const RFO_T *u = F + c * lda;
+            x[c] = x[c] / u[c];
+            RFO_T xc = x[c];
+            for (int64_t r = 0; r < c; ++r) x[r] = RFO_FMA(-u[r], xc, x[r]);
+        }
+    }
+}
+
+/* ---- src/butterflylu.jl:59-91  🦋mul_level!(A, u, v) ------------------------------------------
+ * One butterfly level on the M x N block A (M, N even): with B_u = [D(u1) D(u2); D(u1) -D(u2)]
+ * (u1/u2 = halves of u) this is A <- B_u' A B_v, written exactly as the reference's eight
+ * additions and the (u * C) * v products (left-to-right, :85-88). */
+static void RFO_(rfo_butterfly_level)(RFO_T *A, int64_t M, int64_t N, int64_t lda, const RFO_T *u,
+                                      const RFO_T *v)
+{
+    int64_t Mh = M / 2, Nh = N / 2;
+    for (int64_t n = 0; n < Nh; ++n) {
+        for (int64_t m = 0; m < Mh; ++m) {
+            RFO_T A11 = A[m + n * lda], A21 = A[m + Mh + n * lda];
+            RFO_T A12 = A[m + (n + Nh) * lda], A22 = A[m + Mh + (n + Nh) * lda];
+            RFO_T T1 = A11 + A12, T2 = A21 + A22, T3 = A11 - A12, T4 = A21 - A22;
+            RFO_T C11 = T1 + T2, C21 = T1 - T2, C12 = T3 + T4, C22 = T3 - T4;
+            RFO_T u1 = u[m], u2 = u[m + Mh], v1 = v[n], v2 = v[n + Nh];
+            A[m + n * lda] = u1 * C11 * v1;
+            A[m + Mh + n * lda] = u2 * C21 * v1;
+            A[m + (n + Nh) * lda] = u1 * C12 * v2;
+            A[m + Mh + (n + Nh) * lda] = u2 * C22 * v2;
+        }
+    }
+}
+
+/* ---- src/butterflylu.jl:93-113  🦋mul!(A, uv) ---------------------------------------------------
+ * Two levels: the four quadrants with (U1|U2, V1|V2) = uv[0:M/2], uv[M:3M/2] / uv[M/2:M],
+ * uv[3M/2:2M], then the whole matrix with U = uv[2M:3M], V = uv[3M:4M].  M % 4 == 0. */
+void RFO_(rfo_butterfly_mul)(RFO_T *A, int64_t M, int64_t lda, const RFO_T *uv)
+{
+    int64_t Mh = M / 2;
+    const RFO_T *U1 = uv, *V1 = uv + Mh, *U2 = uv + M, *V2 = uv + M + Mh;
+    RFO_(rfo_butterfly_level)(A, Mh, Mh, lda, U1, V1);
+    RFO_(rfo_butterfly_level)(A + Mh, Mh, Mh, lda, U2, V1);
+    RFO_(rfo_butterfly_level)(A + Mh * lda, Mh, Mh, lda, U1, V2);
+    RFO_(rfo_butterfly_level)(A + Mh + Mh * lda, Mh, Mh, lda, U2, V2);
+    RFO_(rfo_butterfly_level)(A, M, M, lda, uv + 2 * M, uv + 3 * M);
 }
 
 /* Kernel-level entry points so the tests can check each CUDA kernel against the matching
  * restated loop in isolation. */
 int64_t RFO_(rfo_panel)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv, int64_t info)
-{ return RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, n < m ? n : m, info); }
+{ return RFO_(rfo_generic_lufact)(A, m, n, lda, ipiv, n < m ? n : m, info, 1); }
+int64_t RFO_(rfo_panel_nopiv)(RFO_T *A, int64_t m, int64_t n, int64_t lda, int64_t info)
+{ return RFO_(rfo_generic_lufact)(A, m, n, lda, (int64_t *)0, n < m ? n : m, info, 0); }
 void RFO_(rfo_laswp)(RFO_T *A, int64_t ncols, int64_t lda, const int64_t *ipiv, int64_t np)
 { RFO_(rfo_apply_permutation)(ipiv, np, A, ncols, lda, 1); }
 void RFO_(rfo_trsm)(const RFO_T *L, int64_t k, RFO_T *B, int64_t nrhs, int64_t lda, int threads)

@@ -9,6 +9,12 @@ reference's Julia API (paths relative to /root/reference):
 ``lu_(A, ipiv, pivot, ...)``    src/lu.jl:67-83 and :97-130 (``lu!``) -- factor in place
 ``LU``                          LinearAlgebra.LU built at src/lu.jl:129 (factors / ipiv / info, L U p)
 ``SingularException``           raised by ``checknonsingular(info)`` at src/lu.jl:128 when ``check``
+``NotIPIV`` / ``pivot=False``   src/lu.jl:27-65: unpivoted factorization with the lazy identity pivot vector
+``ldiv_(F, B)``                 ``ldiv!(F, B)`` (LinearAlgebra; NotIPIV overload src/lu.jl:60-64)
+``ButterflyWorkspace`` /        src/butterflylu.jl:20-55 (``🦋workspace`` / ``🦋solve!``), ``butterfly_mul_``
+``butterfly_solve_``            = ``🦋mul!`` (:93-113)
+``Adjoint`` / ``Transpose``     src/lu.jl:85-87
+``lu_batched_``                 ``lu!`` over a strided batch of small matrices (README.md:34-35 workload)
 ===========================  =====================================================================
 
 Arrays follow Julia's layout: column-major (Fortran-ordered) ``float64`` / ``float32``.  Pivots are
@@ -29,8 +35,10 @@ from . import _lib
 from ._lib import rfb_opts  # noqa: F401  (re-export)
 
 __all__ = [
-    "lu", "lu_", "ldiv_", "LU", "SingularException", "RfbError", "Context", "default_context", "DeviceMatrix",
-    "nsplit", "RowMaximum", "NoPivot",
+    "lu", "lu_", "ldiv_", "LU", "SingularException", "ZeroPivotException", "RfbError", "Context", "default_context",
+    "DeviceMatrix", "nsplit", "RowMaximum", "NoPivot", "NotIPIV", "Adjoint", "Transpose", "AdjointLU",
+    "ButterflyWorkspace", "butterfly_workspace", "butterfly_solve_", "butterfly_mul_", "butterfly_generate_random",
+    "lu_batched_", "lu_batched",
 ]
 
 
@@ -51,6 +59,68 @@ class SingularException(ArithmeticError):
     def __init__(self, info: int):
         super().__init__(f"matrix is singular to working precision: zero pivot at column {info}")
         self.info = info
+
+
+class ZeroPivotException(ArithmeticError):
+    """LinearAlgebra.ZeroPivotException(k): what ``checknonsingular`` throws for the NEGATIVE info an
+    unpivoted factorization reports on Julia >= 1.11 (src/lu.jl:24-25, :323-326)."""
+
+    def __init__(self, info: int):
+        super().__init__(f"factorization encountered one or more zero pivots (first at column {info}); "
+                         "consider switching to a pivoted LU factorization")
+        self.info = info
+
+
+def _checknonsingular(info: int):
+    """LinearAlgebra.checknonsingular (called at src/lu.jl:128)."""
+    if info > 0:
+        raise SingularException(info)
+    if info < 0:
+        raise ZeroPivotException(-info)
+
+
+class NotIPIV:
+    """src/lu.jl:27-32: the lazy identity pivot vector of an unpivoted factorization (``ipiv[i] == i``)."""
+
+    def __init__(self, n: int):
+        self.len = int(n)
+
+    def __len__(self):
+        return self.len
+
+    @property
+    def size(self):
+        return self.len
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return np.arange(1, self.len + 1, dtype=np.int64)[i]
+        if not -self.len <= i < self.len:
+            raise IndexError(i)
+        return (i % self.len) + 1
+
+    def __iter__(self):
+        return iter(range(1, self.len + 1))
+
+    def __array__(self, dtype=None, copy=None):
+        return np.arange(1, self.len + 1, dtype=dtype or np.int64)
+
+    def __eq__(self, other):
+        return np.array_equal(np.asarray(self), np.asarray(other))
+
+    def __repr__(self):
+        return f"NotIPIV({self.len})"
+
+
+class Adjoint:
+    """Lazy ``A'`` (LinearAlgebra.Adjoint); ``lu(Adjoint(A)) == AdjointLU(lu(A))`` (src/lu.jl:85-87)."""
+
+    def __init__(self, parent: np.ndarray):
+        self.parent = parent
+
+
+class Transpose(Adjoint):
+    """Lazy ``transpose(A)``; identical to Adjoint for the real element types this library handles."""
 
 
 class RowMaximum:   # LinearAlgebra.RowMaximum(), src/lu.jl:13
@@ -280,21 +350,40 @@ class LU:
         return f"LU(factors={self.factors.shape} {self.factors.dtype}, info={self.info})"
 
 
+class AdjointLU:
+    """``adjoint(F)`` / ``transpose(F)`` of a factorization (src/lu.jl:85-87): ``parent`` factors the parent
+    matrix, i.e. ``A' == (P' L U)' = U' L' P``."""
+
+    def __init__(self, parent: LU):
+        self.parent = parent
+
+    @property
+    def info(self):
+        return self.parent.info
+
+    @property
+    def issuccess(self):
+        return self.parent.issuccess
+
+    def __repr__(self):
+        return f"AdjointLU({self.parent!r})"
+
+
 # ----------------------------------------------------------------------------------------------
 # lu / lu!
 # ----------------------------------------------------------------------------------------------
 def _make_opts(mem_space=_lib.RFB_MEM_HOST, leaf_width=0, f32_mode=0, trsm_block=0, gemm_path=0,
-               laswp_path=0) -> rfb_opts:
+               laswp_path=0, no_pivot=0) -> rfb_opts:
     o = rfb_opts()
     o.mem_space, o.leaf_width, o.f32_mode = mem_space, leaf_width, f32_mode
-    o.trsm_block, o.gemm_path, o.laswp_path = trsm_block, gemm_path, laswp_path
+    o.trsm_block, o.gemm_path, o.laswp_path, o.no_pivot = trsm_block, gemm_path, laswp_path, int(no_pivot)
     return o
 
 
-def lu_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check=True,
+def lu_(A, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check=True,
         blocksize: Optional[int] = None, threshold: Optional[int] = None, ctx: Optional[Context] = None,
         leaf_width: int = 0, f32_mode: int = 0, trsm_block: int = 0, gemm_path: int = 0,
-        laswp_path: int = 0) -> LU:
+        laswp_path: int = 0):
     """``RecursiveFactorization.lu!`` (src/lu.jl:67-83 and :97-130): factor ``A`` in place.
 
     ``A`` must be a column-major float64/float32 matrix (it is overwritten with L\\U and returned
@@ -303,10 +392,15 @@ def lu_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, thread=Fal
     ``blocksize``/``threshold`` tune the reference's CPU register kernel and are accepted and
     ignored -- the analogous GPU knob is ``leaf_width``.  ``check=True`` raises
     ``SingularException`` when ``info > 0`` like ``checknonsingular`` (src/lu.jl:128).
+
+    ``pivot=False`` / ``NoPivot()`` (src/lu.jl:27-65): no row interchanges; the returned ``ipiv`` is a
+    ``NotIPIV`` unless the caller passed a vector, which is then filled with ``1:min(m,n)`` (:107-113); a
+    zero pivot gives NEGATIVE ``info`` (Julia >= 1.11, :24-25) and, with ``check``, ``ZeroPivotException``.
     """
-    if not _normalize_pivot(pivot):
-        raise NotImplementedError(
-            "pivot=Val(false)/NoPivot() (src/lu.jl:27-65) is outside the B200 hot path; no fallback is provided")
+    if isinstance(A, Adjoint):                                    # src/lu.jl:85-87
+        return AdjointLU(lu_(A.parent, ipiv, pivot, thread, check=check, ctx=ctx, leaf_width=leaf_width,
+                             f32_mode=f32_mode, trsm_block=trsm_block, gemm_path=gemm_path, laswp_path=laswp_path))
+    piv = _normalize_pivot(pivot)
     if not isinstance(A, np.ndarray) or A.ndim != 2:
         raise TypeError("A must be a 2-D numpy array")
     if A.dtype not in (np.float64, np.float32):
@@ -317,7 +411,12 @@ def lu_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, thread=Fal
                         "use lu() to factor a copy of any layout")
     mn = min(m, n)
     if ipiv is None:
-        ipiv = np.empty(mn, dtype=np.int64)                     # init_pivot, src/lu.jl:40
+        ipiv = np.empty(mn, dtype=np.int64) if piv else NotIPIV(mn)      # init_pivot, src/lu.jl:33-40
+    elif isinstance(ipiv, NotIPIV):
+        if piv:
+            raise TypeError("NotIPIV is only valid with pivot=False")
+        if ipiv.len != mn:
+            raise ValueError(f"ipiv has length {ipiv.len}, expected min(m, n) = {mn}")
     else:
         if not isinstance(ipiv, np.ndarray) or ipiv.dtype != np.int64 or ipiv.ndim != 1 or \
                 not ipiv.flags.c_contiguous:
@@ -326,12 +425,12 @@ def lu_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, thread=Fal
             raise ValueError(f"ipiv has length {ipiv.size}, expected min(m, n) = {mn}")
     ctx = ctx or default_context()
     info = C.c_int64(0)
-    lda = max(m, 1) if A.flags.f_contiguous else max(m, 1)
-    opts = _make_opts(_lib.RFB_MEM_HOST, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path)
-    ctx.lu_raw(A.ctypes.data if A.size else 0, m, n, lda, ipiv.ctypes.data if mn else 0, C.addressof(info),
-               A.dtype, opts)
-    if check and info.value > 0:
-        raise SingularException(info.value)
+    lda = max(m, 1)
+    opts = _make_opts(_lib.RFB_MEM_HOST, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot=not piv)
+    ipiv_ptr = ipiv.ctypes.data if (isinstance(ipiv, np.ndarray) and mn) else 0
+    ctx.lu_raw(A.ctypes.data if A.size else 0, m, n, lda, ipiv_ptr, C.addressof(info), A.dtype, opts)
+    if check:
+        _checknonsingular(info.value)
     return LU(A, ipiv, info.value)
 
 
@@ -350,22 +449,159 @@ def ldiv_(F: LU, B: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
     if not f.flags.f_contiguous:
         f = np.asfortranarray(f)
     nrhs = 1 if B.ndim == 1 else B.shape[1]
-    ipiv = np.ascontiguousarray(F.ipiv, dtype=np.int64)
+    # NotIPIV: both legs are plain triangular solves, no interchanges (src/lu.jl:60-64)
+    ipiv = None if isinstance(F.ipiv, NotIPIV) else np.ascontiguousarray(F.ipiv, dtype=np.int64)
     ctx = ctx or default_context()
     lib = ctx._lib
     fn = lib.rfb_solve_f64 if f.dtype == np.float64 else lib.rfb_solve_f32
     opts = _make_opts(_lib.RFB_MEM_HOST)
-    ctx._check(fn(ctx.handle, C.c_void_p(f.ctypes.data), n, max(n, 1), C.c_void_p(ipiv.ctypes.data),
+    ctx._check(fn(ctx.handle, C.c_void_p(f.ctypes.data), n, max(n, 1),
+                  C.c_void_p(ipiv.ctypes.data) if ipiv is not None else None,
                   C.c_void_p(B.ctypes.data), nrhs, max(n, 1), C.byref(opts)))
     return B
 
 
-def lu(A, pivot=True, thread=False, **kwargs) -> LU:
+def lu(A, pivot=True, thread=False, **kwargs):
     """``RecursiveFactorization.lu`` (src/lu.jl:19-21): ``lu!(copy(A), ...)``."""
+    if isinstance(A, Adjoint):                                    # src/lu.jl:85-87
+        return AdjointLU(lu(A.parent, pivot, thread, **kwargs))
     A = np.asarray(A)
     if A.ndim != 2:
         raise TypeError("A must be a matrix")
     return lu_(np.array(A, order="F", copy=True), None, pivot, thread, **kwargs)
+
+
+# ----------------------------------------------------------------------------------------------
+# butterfly solver (src/butterflylu.jl)
+# ----------------------------------------------------------------------------------------------
+def butterfly_generate_random(n: int, dtype=np.float64, seed: int = 888) -> np.ndarray:
+    """``🦋generate_random!`` (src/butterflylu.jl:9-19): the 4n butterfly values exp(x)/2, x ~ U(-0.05, 0.05).
+
+    The reference draws them from VectorizedRNG's Xoshift stream, whose output depends on the host's SIMD
+    width (test/runtests.jl:143-152) and cannot be reproduced outside Julia; this draws from numpy's
+    ``default_rng(seed)`` (default seed 888 like the reference's ``Val(888)``)."""
+    rng = np.random.default_rng(seed)
+    return (0.5 * np.exp(-0.05 + 0.1 * rng.random(4 * n))).astype(dtype)
+
+
+class ButterflyWorkspace:
+    """``🦋workspace(A, b)`` (src/butterflylu.jl:20-43): the matrix, right-hand side and random butterflies of
+    one solve.  Unlike the reference it does not materialise dense ``U``/``V`` (:149-178) -- the device applies
+    the butterflies in their factored O(n) form -- and padding to a multiple of 4 (``pad!``, :180-197) happens
+    inside the library on the device copy."""
+
+    def __init__(self, A: np.ndarray, b: np.ndarray, seed: int = 888, uv: Optional[np.ndarray] = None):
+        if not isinstance(A, np.ndarray) or A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise TypeError("A must be a square numpy matrix")
+        if A.dtype not in (np.float64, np.float32):
+            raise TypeError(f"eltype {A.dtype} is not supported on the B200 path (Float64/Float32 only); no fallback")
+        self.n = A.shape[0]
+        self.A = np.asfortranarray(A)
+        self.b = np.array(b, dtype=A.dtype, order="F", copy=True)
+        if self.b.shape[0] != self.n or self.b.ndim not in (1, 2):
+            raise ValueError("b must have n rows")
+        npad = self.n if self.n % 4 == 0 else self.n + (4 - self.n % 4)
+        self.ws = butterfly_generate_random(npad, A.dtype, seed) if uv is None else np.ascontiguousarray(uv, dtype=A.dtype)
+        if self.ws.size != 4 * npad:
+            raise ValueError(f"uv must hold 4 * {npad} values")
+        self.out = np.empty_like(self.b)
+        self.info = 0
+
+
+butterfly_workspace = ButterflyWorkspace       # src/butterflylu.jl:57
+
+
+def butterfly_solve_(ws: ButterflyWorkspace, thread=False, ctx: Optional[Context] = None) -> np.ndarray:
+    """``🦋solve!(workspace, thread)`` (src/butterflylu.jl:45-55): transform, unpivoted recursive LU, two
+    triangular solves, back-transform -- all on the GPU.  Returns ``ws.out`` (the solution of ``A x = b``)."""
+    ctx = ctx or default_context()
+    lib = ctx._lib
+    fn = lib.rfb_butterfly_solve_f64 if ws.A.dtype == np.float64 else lib.rfb_butterfly_solve_f32
+    n = ws.n
+    ws.out[...] = ws.b
+    nrhs = 1 if ws.out.ndim == 1 else ws.out.shape[1]
+    info = C.c_int64(0)
+    opts = _make_opts(_lib.RFB_MEM_HOST)
+    ctx._check(fn(ctx.handle, C.c_void_p(ws.A.ctypes.data), n, max(n, 1), C.c_void_p(ws.out.ctypes.data), nrhs, max(n, 1),
+                  C.c_void_p(ws.ws.ctypes.data), C.byref(info), C.byref(opts)))
+    ws.info = info.value
+    _checknonsingular(info.value)              # lu!(A, Val(false), thread) checks by default (:48)
+    return ws.out
+
+
+def butterfly_mul_(A: np.ndarray, uv: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
+    """``🦋mul!(A, uv)`` (src/butterflylu.jl:93-113): overwrite the square column-major ``A`` (size % 4 == 0)
+    with ``U' A V``."""
+    if not isinstance(A, np.ndarray) or A.ndim != 2 or A.shape[0] != A.shape[1] or not A.flags.f_contiguous:
+        raise TypeError("A must be a square column-major numpy matrix")
+    n = A.shape[0]
+    if n % 4:
+        raise ValueError("butterfly_mul_ needs a size divisible by 4")
+    uv = np.ascontiguousarray(uv, dtype=A.dtype)
+    if uv.size != 4 * n:
+        raise ValueError(f"uv must hold 4 * {n} values")
+    ctx = ctx or default_context()
+    lib = ctx._lib
+    fn = lib.rfb_butterfly_mul_f64 if A.dtype == np.float64 else lib.rfb_butterfly_mul_f32
+    d_a, d_uv = ctx.malloc(max(A.nbytes, 16)), ctx.malloc(max(uv.nbytes, 16))
+    try:
+        ctx.h2d(d_a, A)
+        ctx.h2d(d_uv, uv)
+        ctx._check(fn(ctx.handle, C.c_void_p(d_a), n, max(n, 1), C.c_void_p(d_uv)))
+        ctx.d2h(A, d_a)
+        ctx.sync()
+    finally:
+        ctx.free(d_a)
+        ctx.free(d_uv)
+    return A
+
+
+# ----------------------------------------------------------------------------------------------
+# batched small factorizations
+# ----------------------------------------------------------------------------------------------
+def lu_batched_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, *, check=True,
+                ctx: Optional[Context] = None):
+    """``lu!`` on every matrix of a batch: ``A`` has shape (batch, m, n) with each ``A[b]`` column-major
+    (e.g. ``np.empty((batch, n, m)).transpose(0, 2, 1)``), is overwritten with the packed factors and returned
+    as a list of ``LU`` views.  One launch factors all matrices when n <= 64 and m <= 128."""
+    piv = _normalize_pivot(pivot)
+    if not isinstance(A, np.ndarray) or A.ndim != 3 or A.dtype not in (np.float64, np.float32):
+        raise TypeError("A must be a 3-D float64/float32 numpy array (batch, m, n)")
+    batch, m, n = A.shape
+    it = A.itemsize
+    if batch and m and n:
+        if A.strides[1] != it or A.strides[2] < m * it or A.strides[2] % it or A.strides[0] % it or \
+                (batch > 1 and A.strides[0] < A.strides[2] * n) or not A.flags.writeable:
+            raise TypeError("each A[b] must be a writeable column-major matrix (strides (s, itemsize, lda*itemsize))")
+    mn = min(m, n)
+    if piv:
+        if ipiv is None:
+            ipiv = np.empty((batch, mn), dtype=np.int64)
+        elif ipiv.dtype != np.int64 or ipiv.shape != (batch, mn) or not ipiv.flags.c_contiguous:
+            raise TypeError("ipiv must be a C-contiguous int64 array of shape (batch, min(m, n))")
+    info = np.zeros(batch, dtype=np.int64)
+    ctx = ctx or default_context()
+    lib = ctx._lib
+    fn = lib.rfb_lu_batched_f64 if A.dtype == np.float64 else lib.rfb_lu_batched_f32
+    lda = A.strides[2] // it if (m and n) else max(m, 1)
+    stride = A.strides[0] // it if (batch and m and n) else lda * max(n, 1)
+    opts = _make_opts(_lib.RFB_MEM_HOST, no_pivot=not piv)
+    ctx._check(fn(ctx.handle, C.c_void_p(A.ctypes.data) if A.size else None, m, n, lda, stride, batch,
+                  C.c_void_p(ipiv.ctypes.data) if (piv and ipiv.size) else None, C.c_void_p(info.ctypes.data), C.byref(opts)))
+    if check:
+        for v in info:
+            _checknonsingular(int(v))
+    return [LU(A[b], ipiv[b] if piv else NotIPIV(mn), int(info[b])) for b in range(batch)]
+
+
+def lu_batched(A, pivot=True, **kwargs):
+    """Factor copies: ``A`` is any (batch, m, n) array-like."""
+    A = np.asarray(A)
+    if A.ndim != 3:
+        raise TypeError("A must be (batch, m, n)")
+    buf = np.empty((A.shape[0], A.shape[2], A.shape[1]), dtype=A.dtype).transpose(0, 2, 1)
+    buf[...] = A
+    return lu_batched_(buf, None, pivot, **kwargs)
 
 
 # ----------------------------------------------------------------------------------------------

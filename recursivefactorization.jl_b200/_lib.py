@@ -30,7 +30,8 @@ class rfb_opts(C.Structure):
         ("trsm_block", C.c_int32),
         ("gemm_path", C.c_int32),
         ("laswp_path", C.c_int32),
-        ("reserved", C.c_int32 * 10),
+        ("no_pivot", C.c_int32),
+        ("reserved", C.c_int32 * 9),
     ]
 
 
@@ -59,6 +60,16 @@ SIGNATURES = {
     "rfb_trsm_lunn_f32": (_int, [_p, _p, _i64, _p, _i64, _i64]),
     "rfb_solve_f64": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, C.POINTER(rfb_opts)]),
     "rfb_solve_f32": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, C.POINTER(rfb_opts)]),
+    "rfb_panel_getrf_nopiv_f64": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64]),
+    "rfb_panel_getrf_nopiv_f32": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64]),
+    "rfb_butterfly_mul_f64": (_int, [_p, _p, _i64, _i64, _p]),
+    "rfb_butterfly_mul_f32": (_int, [_p, _p, _i64, _i64, _p]),
+    "rfb_butterfly_vec_f64": (_int, [_p, _p, _i64, _i64, _i64, _p, _int]),
+    "rfb_butterfly_vec_f32": (_int, [_p, _p, _i64, _i64, _i64, _p, _int]),
+    "rfb_butterfly_solve_f64": (_int, [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
+    "rfb_butterfly_solve_f32": (_int, [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
+    "rfb_lu_batched_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
+    "rfb_lu_batched_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_range_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_laswp_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),

@@ -1,0 +1,4 @@
+// Batched small-matrix LU (one CTA per matrix), Float32 instantiation (see panel_impl.cuh).
+#define RFB_PANEL_T float
+#define RFB_PANEL_BATCHED 1
+#include "panel_impl.cuh"

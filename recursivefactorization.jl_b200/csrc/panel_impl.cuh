@@ -137,17 +137,29 @@ struct PanelPermOut {
 // instructions for NB = 64, spent ~3 us per column in instruction-fetch stalls.)  Finished values
 // leave the window through a shared-memory tile fin[column][thread] and are written to global
 // memory once, at the row's final position.
-template <typename T, int NB, int THREADS>
+//
+// BATCHED = true turns the same kernel into the batched small-matrix LU (the
+// reference's own small-matrix path is this unblocked loop, src/lu.jl:125-126): one CTA per matrix
+// (blockIdx.x = matrix, up to THREADS rows and NB columns, fat shapes included -- the loop runs
+// min(m, n) pivot steps over all n columns), no inter-CTA exchange.
+template <typename T, int NB, int THREADS, bool BATCHED = false>
 __global__ void __launch_bounds__(THREADS, 1)
 panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ ipiv,
              long long ipiv_add, long long *__restrict__ info, long long col_offset,
-             RfbPanelXchg *__restrict__ x, unsigned int epoch_base, PanelPermOut perm) {
+             RfbPanelXchg *__restrict__ x, unsigned int epoch_base, PanelPermOut perm,
+             long long batch_stride_a, long long batch_stride_p) {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char panel_smem[];
     T *fin = reinterpret_cast<T *>(panel_smem);                 // [NB][THREADS]
     __shared__ PanelShared<T, NB, WARPS> sh;
 
-    const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+    const int G = BATCHED ? 1 : (int)gridDim.x, bid = BATCHED ? 0 : (int)blockIdx.x, tid = threadIdx.x;
+    if (BATCHED) {
+        A += (long long)blockIdx.x * batch_stride_a;
+        ipiv += (long long)blockIdx.x * batch_stride_p;
+        info += blockIdx.x;
+    }
+    const int npiv = m < n ? m : n;                             // pivot steps (length(ipiv), src/lu.jl:292)
     const int lane = tid & 31, warp = tid >> 5;
     const int row = bid * THREADS + tid;
 
@@ -163,7 +175,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
     __syncthreads();
 
 #pragma unroll 1
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < npiv; ++k) {
         const int par = k & 1;
         const int rem = n - k;                                   // live width of the window
         const unsigned int epoch = epoch_base + (unsigned int)k;
@@ -288,6 +300,52 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
     if (perm.width != nullptr && bid == 0 && tid == 0) perm.width[0] = n;
 }
 
+#ifdef RFB_PANEL_BATCHED
+// ---- batched small-matrix launcher (panel_batched_f64.cu / _f32.cu) ---------------------------------
+template <typename T, int NB, int THREADS>
+int launch_batched_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t stride_a, int64_t batch, int64_t *ipiv,
+                        int64_t *info) {
+    auto kern = panel_kernel<T, NB, THREADS, true>;
+    constexpr size_t smem = sizeof(T) * NB * THREADS;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
+    const int64_t mn = m < n ? m : n;
+    const double flops = mn == n ? (double)m * n * n - (double)n * n * n / 3.0 : (double)n * m * m - (double)m * m * m / 3.0;
+    RfbLaunchScope scope(ctx, RFB_KC_PANEL, flops * (double)batch);
+    PanelPermOut perm{nullptr, nullptr, nullptr, 0};
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535 * 32) {       // (grid.x limit is 2^31-1; chunk anyway)
+        const int64_t nb = batch - b0 < 65535 * 32 ? batch - b0 : 65535 * 32;
+        kern<<<(unsigned)nb, THREADS, smem, ctx->stream>>>(A + b0 * stride_a, m, n, (long long)lda, (long long *)(ipiv + b0 * mn), 0ll,
+                                                          (long long *)(info + b0), 0ll, nullptr, 0u, perm, (long long)stride_a,
+                                                          (long long)mn);
+        RFB_CUDA(ctx, cudaGetLastError());
+    }
+    return RFB_OK;
+}
+
+template <typename T, int THREADS>
+int launch_batched_threads(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t stride_a, int64_t batch, int64_t *ipiv,
+                           int64_t *info) {
+    if (n <= 16) return launch_batched_inst<T, 16, THREADS>(ctx, A, m, n, lda, stride_a, batch, ipiv, info);
+    if (n <= 32) return launch_batched_inst<T, 32, THREADS>(ctx, A, m, n, lda, stride_a, batch, ipiv, info);
+    return launch_batched_inst<T, 64, THREADS>(ctx, A, m, n, lda, stride_a, batch, ipiv, info);
+}
+
+}  // namespace
+
+// One CTA per matrix; needs n <= 64 and m <= 128 (the caller falls back to the recursive driver otherwise).
+// info[b] must be zeroed by the caller (the kernel only writes a first zero pivot).
+template <typename T>
+int rfb_launch_panel_batched(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                             int64_t *ipiv_dev, int64_t *info_dev) {
+    if (batch <= 0 || m <= 0 || n <= 0) return RFB_OK;
+    if (n > RFB_MAX_NB || m > 128) return ctx->fail(RFB_ERR_UNSUPPORTED, "batched kernel handles up to 128 x 64");
+    if (m <= 32) return launch_batched_threads<T, 32>(ctx, A, (int)m, (int)n, lda, stride_a, batch, ipiv_dev, info_dev);
+    if (m <= 64) return launch_batched_threads<T, 64>(ctx, A, (int)m, (int)n, lda, stride_a, batch, ipiv_dev, info_dev);
+    return launch_batched_threads<T, 128>(ctx, A, (int)m, (int)n, lda, stride_a, batch, ipiv_dev, info_dev);
+}
+template int rfb_launch_panel_batched<RFB_PANEL_T>(rfb_ctx *, RFB_PANEL_T *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t *, int64_t *);
+
+#else  // !RFB_PANEL_BATCHED
 // How many CTAs of this instantiation can be co-resident (what a cooperative launch accepts).
 template <typename T, int NB, int THREADS>
 int panel_capacity(rfb_ctx *ctx) {
@@ -315,7 +373,8 @@ int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ip
     long long *ipiv_ = (long long *)ipiv, *info_ = (long long *)info;
     RfbPanelXchg *x = ctx->xchg;
     unsigned int epoch = ctx->panel_epoch;
-    void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch, &perm};
+    long long zero_ = 0;
+    void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch, &perm, &zero_, &zero_};
     constexpr size_t smem = sizeof(T) * NB * THREADS;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
     RfbLaunchScope scope(ctx, RFB_KC_PANEL, (double)m * n * n - (double)n * n * n / 3.0);
@@ -381,3 +440,4 @@ int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m) {
 template int rfb_panel_leaf_for_rows<RFB_PANEL_T>(rfb_ctx *, int64_t);
 
 template int rfb_launch_panel<RFB_PANEL_T>(rfb_ctx *, RFB_PANEL_T *, int64_t, int64_t, int64_t, int64_t *, int64_t, int64_t *, int64_t, int64_t);
+#endif  // RFB_PANEL_BATCHED

@@ -25,6 +25,7 @@ namespace {
 
 struct LuPlan {
     int leaf;
+    bool pivot = true;     // false: pivot = Val(false) (src/lu.jl:27-65), no interchanges, negative info
     bool lists;            // K1 emits row-exchange lists and K2 consumes them (default)
     const rfb_opts *opts;
     // early download (host mode): rows [0, n1) of the root are final long before the factorization ends
@@ -71,13 +72,14 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
     const int64_t mm = m - c0;            // rows of the node
     if (n <= plan.leaf) {                 // :192-195 leaf -> K1
         RFB_TRY(need_cols(ctx, plan, c0 + n));
+        if (!plan.pivot) return rfb_launch_panel_nopiv<T>(ctx, A, mm, n, lda, info, c0);
         return rfb_launch_panel<T>(ctx, A, mm, n, lda, ipiv + c0, c0, info, c0, plan.lists ? c0 : -1);
     }
     const int64_t n1 = rfb_nsplit<T>(n), n2 = n - n1;                                   // :196-198
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n1, ipiv, info, plan));                    // :229
     T *AR = A + n1 * lda;
     RFB_TRY(need_cols(ctx, plan, c0 + n));
-    RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));                          // :233
+    if (plan.pivot) RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));          // :233
     RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
     if (plan.host_A && at_root && n1 >= 1024) {
         // root node, host mode: rows [0, n1) of ALL root columns (L11\U11 and U12) are final now -- the
@@ -91,6 +93,7 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
     }
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan));               // :244
+    if (!plan.pivot) return RFB_OK;
     return lu_swap<T>(ctx, A + n1, n1, lda, ipiv, c0 + n1, n2, plan);                   // :246
 }
 
@@ -106,9 +109,10 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     plan.host_lda = host_lda;
     plan.host_m = m;
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
+    plan.pivot = !(opts && opts->no_pivot);
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
         return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
-    {   // very tall matrices: narrow the leaf until one row per thread fits the cooperative grid
+    if (plan.pivot) {   // very tall matrices: narrow the leaf until one row per thread fits the cooperative grid
         const int fit = rfb_panel_leaf_for_rows<T>(ctx, m);
         if (fit == 0)
             return ctx->fail(RFB_ERR_UNSUPPORTED, "%lld rows exceed the panel kernel's one-row-per-thread capacity", (long long)m);
@@ -117,7 +121,8 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t), ctx->stream));
     const int64_t mn = m < n ? m : n;
     if (mn == 0) return RFB_OK;
-    plan.lists = !(opts && opts->laswp_path == 1);
+    plan.lists = plan.pivot && !(opts && opts->laswp_path == 1);
+    if (!plan.pivot && d_ipiv) RFB_TRY(rfb_launch_iota(ctx, d_ipiv, mn, 1));               // :107-113
     if (plan.lists) {
         if ((size_t)mn > ctx->perm_cap) {
             if (ctx->perm_external) return ctx->fail(RFB_ERR_ARG, "caller-provided exchange-list buffers are too small");
@@ -141,7 +146,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     if (m < n) {                                                                        // :148-154
         T *AR = dA + m * lda;
         RFB_TRY(need_cols(ctx, plan, n));
-        RFB_TRY(lu_swap<T>(ctx, AR, n - m, lda, d_ipiv, 0, mn, plan));
+        if (plan.pivot) RFB_TRY(lu_swap<T>(ctx, AR, n - m, lda, d_ipiv, 0, mn, plan));
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
     if (early_rows) *early_rows = plan.early_rows;
@@ -196,13 +201,13 @@ int solve_entry(rfb_ctx *ctx, const T *LU, int64_t n, int64_t lda, const int64_t
     if (!ctx) return RFB_ERR_ARG;
     if (n < 0 || nrhs < 0) return ctx->fail(RFB_ERR_ARG, "negative dimension");
     if (n == 0 || nrhs == 0) return RFB_OK;
-    if (!LU || !ipiv || !B) return ctx->fail(RFB_ERR_ARG, "null pointer");
+    if (!LU || !B) return ctx->fail(RFB_ERR_ARG, "null pointer");   // ipiv == NULL: NotIPIV (src/lu.jl:60-64)
     if (lda < n || ldb < n) return ctx->fail(RFB_ERR_ARG, "leading dimension smaller than n");
     RFB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int space = opts ? opts->mem_space : RFB_MEM_HOST;
     if (space == RFB_MEM_DEVICE) {
         if (ldb != lda) return ctx->fail(RFB_ERR_UNSUPPORTED, "device-mode solve needs ldb == lda (one shared leading dimension)");
-        RFB_TRY(rfb_launch_laswp<T>(ctx, B, nrhs, ldb, ipiv, n, 0));
+        if (ipiv) RFB_TRY(rfb_launch_laswp<T>(ctx, B, nrhs, ldb, ipiv, n, 0));
         RFB_TRY(rfb_launch_trsm<T>(ctx, LU, n, B, nrhs, lda, opts));
         return rfb_launch_trsm_upper<T>(ctx, LU, n, B, nrhs, lda, opts);
     }
@@ -218,7 +223,7 @@ int solve_entry(rfb_ctx *ctx, const T *LU, int64_t n, int64_t lda, const int64_t
         }
         ctx->d_mat_cap = need;
     }
-    if ((size_t)n > ctx->d_ipiv_cap) {
+    if (ipiv && (size_t)n > ctx->d_ipiv_cap) {
         if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
         ctx->d_ipiv = nullptr;
         ctx->d_ipiv_cap = 0;
@@ -232,11 +237,188 @@ int solve_entry(rfb_ctx *ctx, const T *LU, int64_t n, int64_t lda, const int64_t
     T *dB = dLU + (size_t)ldd * n;
     RFB_CUDA(ctx, cudaMemcpy2DAsync(dLU, sizeof(T) * ldd, LU, sizeof(T) * lda, sizeof(T) * n, n, cudaMemcpyHostToDevice, ctx->stream));
     RFB_CUDA(ctx, cudaMemcpy2DAsync(dB, sizeof(T) * ldd, B, sizeof(T) * ldb, sizeof(T) * n, nrhs, cudaMemcpyHostToDevice, ctx->stream));
-    RFB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ipiv, ipiv, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-    RFB_TRY(rfb_launch_laswp<T>(ctx, dB, nrhs, ldd, ctx->d_ipiv, n, 0));
+    if (ipiv) {
+        RFB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ipiv, ipiv, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        RFB_TRY(rfb_launch_laswp<T>(ctx, dB, nrhs, ldd, ctx->d_ipiv, n, 0));
+    }
     RFB_TRY(rfb_launch_trsm<T>(ctx, dLU, n, dB, nrhs, ldd, opts));
     RFB_TRY(rfb_launch_trsm_upper<T>(ctx, dLU, n, dB, nrhs, ldd, opts));
     RFB_CUDA(ctx, cudaMemcpy2DAsync(B, sizeof(T) * ldb, dB, sizeof(T) * ldd, sizeof(T) * n, nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RFB_OK;
+}
+
+// 🦋solve!(🦋workspace(A, b)) (src/butterflylu.jl:20-55): pad to a multiple of 4 (:34-38, :180-197),
+// A <- U' A V (:47), NoPivot recursive LU (:48), tmp = U' b (:50), ldiv!(F, tmp) (:51, the NotIPIV
+// overload src/lu.jl:60-64), x = V tmp (:52), out = x[1:n] (:53).
+template <typename T>
+int butterfly_solve_entry(rfb_ctx *ctx, const T *A, int64_t n, int64_t lda, T *B, int64_t nrhs, int64_t ldb,
+                          const T *uv, int64_t *info, const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (n < 0 || nrhs < 0) return ctx->fail(RFB_ERR_ARG, "negative dimension");
+    if (!info) return ctx->fail(RFB_ERR_ARG, "info is null");
+    const int space = opts ? opts->mem_space : RFB_MEM_HOST;
+    if (n == 0) {
+        if (space == RFB_MEM_HOST) *info = 0;
+        return RFB_OK;
+    }
+    if (!A || !uv || (nrhs > 0 && !B)) return ctx->fail(RFB_ERR_ARG, "null pointer");
+    if (lda < n || (nrhs > 0 && ldb < n)) return ctx->fail(RFB_ERR_ARG, "leading dimension smaller than n");
+    if (n > 0x7ffffff0LL) return ctx->fail(RFB_ERR_UNSUPPORTED, "dimension exceeds int32");
+    RFB_CUDA(ctx, cudaSetDevice(ctx->device));
+    rfb_opts o = opts ? *opts : rfb_opts{};
+    o.no_pivot = 1;
+    o.mem_space = RFB_MEM_DEVICE;
+    if (space == RFB_MEM_DEVICE) {
+        // in place on device buffers: the caller has already padded (n % 4 == 0) and shares one leading dimension
+        if (n % 4 != 0) return ctx->fail(RFB_ERR_UNSUPPORTED, "device-mode butterfly solve needs n %% 4 == 0 (pad first, src/butterflylu.jl:180-197)");
+        if (nrhs > 0 && ldb != lda) return ctx->fail(RFB_ERR_UNSUPPORTED, "device-mode butterfly solve needs ldb == lda");
+        T *dA = const_cast<T *>(A);
+        RFB_TRY(rfb_launch_butterfly_mul<T>(ctx, dA, n, lda, uv));
+        RFB_TRY(lu_device<T>(ctx, dA, n, n, lda, nullptr, info, &o));
+        RFB_TRY(rfb_launch_butterfly_vec<T>(ctx, B, n, nrhs, ldb, uv, 0));
+        RFB_TRY(rfb_launch_trsm<T>(ctx, dA, n, B, nrhs, lda, &o));
+        RFB_TRY(rfb_launch_trsm_upper<T>(ctx, dA, n, B, nrhs, lda, &o));
+        return rfb_launch_butterfly_vec<T>(ctx, B, n, nrhs, ldb, uv, 1);
+    }
+    if (space != RFB_MEM_HOST) return ctx->fail(RFB_ERR_ARG, "unknown mem_space %d", space);
+    const int64_t np = (n % 4) ? n + (4 - n % 4) : n;      // padded size (:34-38)
+    const int64_t ldd = np;
+    const size_t need = sizeof(T) * ((size_t)ldd * (size_t)(np + nrhs) + 4 * (size_t)np);
+    if (need > ctx->d_mat_cap) {
+        if (ctx->d_mat) cudaFree(ctx->d_mat);
+        ctx->d_mat = nullptr;
+        ctx->d_mat_cap = 0;
+        if (cudaMalloc(&ctx->d_mat, need) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the butterfly solve", need);
+        }
+        ctx->d_mat_cap = need;
+    }
+    T *dA = reinterpret_cast<T *>(ctx->d_mat);
+    T *dB = dA + (size_t)ldd * np;
+    T *duv = dB + (size_t)ldd * nrhs;
+    if (np != n || nrhs > 0) RFB_CUDA(ctx, cudaMemsetAsync(dA, 0, sizeof(T) * (size_t)ldd * (size_t)(np + nrhs), ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(dA, sizeof(T) * ldd, A, sizeof(T) * lda, sizeof(T) * n, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (np != n) RFB_TRY(rfb_launch_set_diag<T>(ctx, dA, ldd, n, np, T(1)));     // identity corner of pad! (:193-195)
+    if (nrhs > 0)
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(dB, sizeof(T) * ldd, B, sizeof(T) * ldb, sizeof(T) * n, nrhs, cudaMemcpyHostToDevice, ctx->stream));
+    RFB_CUDA(ctx, cudaMemcpyAsync(duv, uv, sizeof(T) * 4 * (size_t)np, cudaMemcpyHostToDevice, ctx->stream));
+    RFB_TRY(rfb_launch_butterfly_mul<T>(ctx, dA, np, ldd, duv));
+    RFB_TRY(lu_device<T>(ctx, dA, np, np, ldd, nullptr, ctx->d_info, &o));
+    if (nrhs > 0) {
+        RFB_TRY(rfb_launch_butterfly_vec<T>(ctx, dB, np, nrhs, ldd, duv, 0));
+        RFB_TRY(rfb_launch_trsm<T>(ctx, dA, np, dB, nrhs, ldd, &o));
+        RFB_TRY(rfb_launch_trsm_upper<T>(ctx, dA, np, dB, nrhs, ldd, &o));
+        RFB_TRY(rfb_launch_butterfly_vec<T>(ctx, dB, np, nrhs, ldd, duv, 1));
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(B, sizeof(T) * ldb, dB, sizeof(T) * ldd, sizeof(T) * n, nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[0], ctx->d_info, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *info = ctx->h_pinned[0];
+    return RFB_OK;
+}
+
+// lu! applied to each matrix of a strided batch (the reference's sweet spot is many
+// small factorizations, README.md:34-35).  Small pivoted matrices (n <= 64, m <= 128) take ONE launch with one
+// CTA per matrix -- the unblocked loop the reference itself uses below its threshold (src/lu.jl:125-126);
+// anything else runs the recursive driver matrix by matrix on the stream.
+template <typename T>
+int lu_batched_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                      int64_t *d_ipiv, int64_t *d_info, const rfb_opts *opts) {
+    const int64_t mn = m < n ? m : n;
+    const bool nopiv = opts && opts->no_pivot;
+    RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t) * (size_t)batch, ctx->stream));
+    if (mn == 0) return RFB_OK;
+    if (!nopiv && n <= RFB_MAX_NB && m <= 128)
+        return rfb_launch_panel_batched<T>(ctx, dA, m, n, lda, stride_a, batch, d_ipiv, d_info);
+    for (int64_t b = 0; b < batch; ++b)
+        RFB_TRY(lu_device<T>(ctx, dA + b * stride_a, m, n, lda, d_ipiv ? d_ipiv + b * mn : nullptr, d_info + b, opts));
+    return RFB_OK;
+}
+
+template <typename T>
+int lu_batched_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch, int64_t *ipiv,
+                     int64_t *info, const rfb_opts *opts) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (m < 0 || n < 0 || batch < 0) return ctx->fail(RFB_ERR_ARG, "negative dimension");
+    if (batch == 0) return RFB_OK;
+    if (!info) return ctx->fail(RFB_ERR_ARG, "info is null");
+    if (lda < (m > 1 ? m : 1)) return ctx->fail(RFB_ERR_ARG, "lda %lld < max(1, m)", (long long)lda);
+    if (batch > 1 && stride_a < lda * n) return ctx->fail(RFB_ERR_ARG, "batch stride %lld < lda * n (matrices overlap)", (long long)stride_a);
+    const int64_t mn = m < n ? m : n;
+    const bool nopiv = opts && opts->no_pivot;
+    if (mn > 0 && (!A || (!ipiv && !nopiv))) return ctx->fail(RFB_ERR_ARG, "A or ipiv is null");
+    if (m > 0x7fffffffLL || n > 0x7fffffffLL) return ctx->fail(RFB_ERR_UNSUPPORTED, "dimension exceeds int32");
+    RFB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int space = opts ? opts->mem_space : RFB_MEM_HOST;
+    if (space == RFB_MEM_DEVICE) return lu_batched_device<T>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts);
+    if (space != RFB_MEM_HOST) return ctx->fail(RFB_ERR_ARG, "unknown mem_space %d", space);
+    if (mn == 0) {
+        for (int64_t b = 0; b < batch; ++b) info[b] = 0;
+        return RFB_OK;
+    }
+    const int64_t ldd = (m + 1) & ~int64_t(1);
+    const int64_t sdd = ldd * n;
+    const size_t need = sizeof(T) * (size_t)sdd * (size_t)batch;
+    if (need > ctx->d_mat_cap) {
+        if (ctx->d_mat) cudaFree(ctx->d_mat);
+        ctx->d_mat = nullptr;
+        ctx->d_mat_cap = 0;
+        if (cudaMalloc(&ctx->d_mat, need) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate %zu bytes of device memory for the batch", need);
+        }
+        ctx->d_mat_cap = need;
+    }
+    if (!nopiv && (size_t)(mn * batch) > ctx->d_ipiv_cap) {
+        if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
+        ctx->d_ipiv = nullptr;
+        ctx->d_ipiv_cap = 0;
+        if (cudaMalloc(&ctx->d_ipiv, sizeof(int64_t) * (size_t)(mn * batch)) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate the device pivot vectors");
+        }
+        ctx->d_ipiv_cap = (size_t)(mn * batch);
+    }
+    if ((size_t)batch > ctx->d_binfo_cap) {
+        if (ctx->d_binfo) cudaFree(ctx->d_binfo);
+        ctx->d_binfo = nullptr;
+        ctx->d_binfo_cap = 0;
+        if (cudaMalloc(&ctx->d_binfo, sizeof(int64_t) * (size_t)batch) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate the device info vector");
+        }
+        ctx->d_binfo_cap = (size_t)batch;
+    }
+    T *dA = reinterpret_cast<T *>(ctx->d_mat);
+    // a dense batch (lda == m, stride == m * n, m even) is one 1-D copy; otherwise one 2-D copy per matrix
+    const bool dense = (lda == ldd && stride_a == sdd);
+    if (dense) {
+        RFB_CUDA(ctx, cudaMemcpyAsync(dA, A, need, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (lda == m && stride_a == m * n) {   // contiguous on the host, padded on the device: one 2-D copy over all columns
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(dA, sizeof(T) * ldd, A, sizeof(T) * m, sizeof(T) * m, (size_t)(n * batch), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int64_t b = 0; b < batch; ++b)
+            RFB_CUDA(ctx, cudaMemcpy2DAsync(dA + b * sdd, sizeof(T) * ldd, A + b * stride_a, sizeof(T) * lda, sizeof(T) * m, n,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RFB_TRY(lu_batched_device<T>(ctx, dA, m, n, ldd, sdd, batch, nopiv ? nullptr : ctx->d_ipiv, ctx->d_binfo, opts));
+    if (dense) {
+        RFB_CUDA(ctx, cudaMemcpyAsync(A, dA, need, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (lda == m && stride_a == m * n) {
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * m, dA, sizeof(T) * ldd, sizeof(T) * m, (size_t)(n * batch), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        for (int64_t b = 0; b < batch; ++b)
+            RFB_CUDA(ctx, cudaMemcpy2DAsync(A + b * stride_a, sizeof(T) * lda, dA + b * sdd, sizeof(T) * ldd, sizeof(T) * m, n,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (nopiv) {
+        if (ipiv) for (int64_t b = 0; b < batch; ++b) for (int64_t i = 0; i < mn; ++i) ipiv[b * mn + i] = i + 1;
+    } else {
+        RFB_CUDA(ctx, cudaMemcpyAsync(ipiv, ctx->d_ipiv, sizeof(int64_t) * (size_t)(mn * batch), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RFB_CUDA(ctx, cudaMemcpyAsync(info, ctx->d_binfo, sizeof(int64_t) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream));
     RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RFB_OK;
 }
@@ -249,7 +431,8 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     if (lda < (m > 1 ? m : 1)) return ctx->fail(RFB_ERR_ARG, "lda %lld < max(1, m) with m = %lld", (long long)lda, (long long)m);
     if (!info) return ctx->fail(RFB_ERR_ARG, "info is null");
     const int64_t mn = m < n ? m : n;
-    if (mn > 0 && (!A || !ipiv)) return ctx->fail(RFB_ERR_ARG, "A or ipiv is null");
+    const bool nopiv = opts && opts->no_pivot;        // ipiv may be NULL then (NotIPIV, src/lu.jl:27-32)
+    if (mn > 0 && (!A || (!ipiv && !nopiv))) return ctx->fail(RFB_ERR_ARG, "A or ipiv is null");
     if (m > 0x7fffffffLL || n > 0x7fffffffLL) return ctx->fail(RFB_ERR_UNSUPPORTED, "dimension exceeds int32");
     RFB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int space = opts ? opts->mem_space : RFB_MEM_HOST;
@@ -274,7 +457,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
         }
         ctx->d_mat_cap = need;
     }
-    if ((size_t)mn > ctx->d_ipiv_cap) {
+    if (!nopiv && (size_t)mn > ctx->d_ipiv_cap) {
         if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
         ctx->d_ipiv = nullptr;
         ctx->d_ipiv_cap = 0;
@@ -309,7 +492,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     cudaPointerAttributes pattr;
     const bool pinned = cudaPointerGetAttributes(&pattr, A) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols,
+    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, nopiv ? nullptr : ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols,
                          (pinned && m >= n) ? A : nullptr, lda, &early_rows, &early_cols));
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
     // download what the early copy (rows [0, early_rows) of the first early_cols columns) did not cover
@@ -325,7 +508,11 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
         RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * lda, dA, sizeof(T) * ldd, sizeof(T) * m, n,
                                         cudaMemcpyDeviceToHost, ctx->stream));
     }
-    RFB_CUDA(ctx, cudaMemcpyAsync(ipiv, ctx->d_ipiv, sizeof(int64_t) * mn, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nopiv) {
+        if (ipiv) for (int64_t i = 0; i < mn; ++i) ipiv[i] = i + 1;            // src/lu.jl:107-113
+    } else {
+        RFB_CUDA(ctx, cudaMemcpyAsync(ipiv, ctx->d_ipiv, sizeof(int64_t) * mn, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[0], ctx->d_info, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     RFB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_pinned[1], &ctx->xchg->error_flag, sizeof(unsigned int),
                                   cudaMemcpyDeviceToHost, ctx->stream));
@@ -398,6 +585,7 @@ int rfb_destroy(rfb_ctx *ctx) {
     if (ctx->xchg) cudaFree(ctx->xchg);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
+    if (ctx->d_binfo) cudaFree(ctx->d_binfo);
     if (ctx->d_mat) cudaFree(ctx->d_mat);
     if (!ctx->perm_external) {
         if (ctx->perm_dst) cudaFree(ctx->perm_dst);
@@ -545,6 +733,50 @@ int rfb_solve_f64(rfb_ctx *ctx, const double *LU, int64_t n, int64_t lda, const 
 int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const int64_t *ipiv, float *B, int64_t nrhs,
                   int64_t ldb, const rfb_opts *opts) {
     return solve_entry<float>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts);
+}
+int rfb_panel_getrf_nopiv_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev, int64_t col_offset) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_panel_nopiv<double>(ctx, A, m, n, lda, info_dev, col_offset);
+}
+int rfb_panel_getrf_nopiv_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev, int64_t col_offset) {
+    RFB_CHECK_CTX(ctx);
+    return rfb_launch_panel_nopiv<float>(ctx, A, m, n, lda, info_dev, col_offset);
+}
+int rfb_butterfly_mul_f64(rfb_ctx *ctx, double *A, int64_t n, int64_t lda, const double *uv_dev) {
+    RFB_CHECK_CTX(ctx);
+    if (!A || !uv_dev) return ctx->fail(RFB_ERR_ARG, "null pointer");
+    return rfb_launch_butterfly_mul<double>(ctx, A, n, lda, uv_dev);
+}
+int rfb_butterfly_mul_f32(rfb_ctx *ctx, float *A, int64_t n, int64_t lda, const float *uv_dev) {
+    RFB_CHECK_CTX(ctx);
+    if (!A || !uv_dev) return ctx->fail(RFB_ERR_ARG, "null pointer");
+    return rfb_launch_butterfly_mul<float>(ctx, A, n, lda, uv_dev);
+}
+int rfb_butterfly_vec_f64(rfb_ctx *ctx, double *B, int64_t n, int64_t nrhs, int64_t ldb, const double *uv_dev, int which) {
+    RFB_CHECK_CTX(ctx);
+    if (!B || !uv_dev || (which != 0 && which != 1)) return ctx->fail(RFB_ERR_ARG, "null pointer or which not in {0, 1}");
+    return rfb_launch_butterfly_vec<double>(ctx, B, n, nrhs, ldb, uv_dev, which);
+}
+int rfb_butterfly_vec_f32(rfb_ctx *ctx, float *B, int64_t n, int64_t nrhs, int64_t ldb, const float *uv_dev, int which) {
+    RFB_CHECK_CTX(ctx);
+    if (!B || !uv_dev || (which != 0 && which != 1)) return ctx->fail(RFB_ERR_ARG, "null pointer or which not in {0, 1}");
+    return rfb_launch_butterfly_vec<float>(ctx, B, n, nrhs, ldb, uv_dev, which);
+}
+int rfb_butterfly_solve_f64(rfb_ctx *ctx, const double *A, int64_t n, int64_t lda, double *B, int64_t nrhs, int64_t ldb,
+                            const double *uv, int64_t *info, const rfb_opts *opts) {
+    return butterfly_solve_entry<double>(ctx, A, n, lda, B, nrhs, ldb, uv, info, opts);
+}
+int rfb_butterfly_solve_f32(rfb_ctx *ctx, const float *A, int64_t n, int64_t lda, float *B, int64_t nrhs, int64_t ldb,
+                            const float *uv, int64_t *info, const rfb_opts *opts) {
+    return butterfly_solve_entry<float>(ctx, A, n, lda, B, nrhs, ldb, uv, info, opts);
+}
+int rfb_lu_batched_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                       int64_t *ipiv, int64_t *info, const rfb_opts *opts) {
+    return lu_batched_entry<double>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts);
+}
+int rfb_lu_batched_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                       int64_t *ipiv, int64_t *info, const rfb_opts *opts) {
+    return lu_batched_entry<float>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts);
 }
 int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift) {
     RFB_CHECK_CTX(ctx);

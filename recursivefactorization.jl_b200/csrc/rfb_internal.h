@@ -56,6 +56,8 @@ struct rfb_ctx {
     void *d_mat = nullptr;                // device matrix for HOST mem_space calls (grow-only)
     size_t d_mat_cap = 0;
     int64_t *h_pinned = nullptr;          // pinned scratch (info + small results)
+    int64_t *d_binfo = nullptr;           // device info words of host-mode batched calls (grow-only)
+    size_t d_binfo_cap = 0;
     // per-panel row-exchange lists written by K1 and consumed by the list-driven K2 (absolute rows)
     int *perm_dst = nullptr, *perm_src = nullptr, *perm_width = nullptr;
     size_t perm_cap = 0;                  // columns the three arrays are sized for
@@ -134,6 +136,21 @@ struct RfbLaunchScope {
 template <typename T>
 int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
                      int64_t ipiv_add, int64_t *info_dev, int64_t col_offset, int64_t perm_row0 = -1);
+// batched small-matrix LU: one CTA per matrix, n <= 64, m <= 128 (panel_batched_*.cu); info must be pre-zeroed
+template <typename T>
+int rfb_launch_panel_batched(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
+                             int64_t *ipiv_dev, int64_t *info_dev);
+// K1' (panel_nopiv.cu): src/lu.jl:290-338 with Pivot = false; negative info on a zero pivot
+template <typename T>
+int rfb_launch_panel_nopiv(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev, int64_t col_offset);
+int rfb_launch_iota(rfb_ctx *ctx, int64_t *p_dev, int64_t n, int64_t first);
+// butterfly.cu: 🦋mul! (src/butterflylu.jl:93-113) and the factored U' b / V b products (:50-52)
+template <typename T>
+int rfb_launch_butterfly_mul(rfb_ctx *ctx, T *A, int64_t M, int64_t lda, const T *uv);
+template <typename T>
+int rfb_launch_butterfly_vec(rfb_ctx *ctx, T *B, int64_t M, int64_t nrhs, int64_t ldb, const T *uv, int which);
+template <typename T>
+int rfb_launch_set_diag(rfb_ctx *ctx, T *A, int64_t lda, int64_t i0, int64_t i1, T value);
 // widest leaf (64, 32 or 16 columns) whose one-row-per-thread cooperative grid can hold m rows; 0 = none
 template <typename T>
 int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m);

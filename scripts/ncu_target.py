@@ -37,3 +37,18 @@ elif what == "gemm":
     for _ in range(2):
         ctx._check(ctx._lib.rfb_gemm_nn_sub_f64(ctx.handle, at(k, k), at(k, 0), at(0, k), m, n, k, lda))
     ctx.sync()
+elif what == "nopiv":
+    n = int(sys.argv[2])
+    a = np.asfortranarray(np.random.default_rng(12).random((n, n)))
+    a[np.arange(n), np.arange(n)] += n / 4
+    d = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
+    d.upload(a)
+    uv = rfb200.butterfly_generate_random(n)
+    duv = ctx.malloc(uv.nbytes); ctx.h2d(duv, uv)
+    ctx._check(ctx._lib.rfb_butterfly_mul_f64(ctx.handle, C.c_void_p(d.ptr), n, n, C.c_void_p(duv)))
+    d.lu(no_pivot=1)
+    ctx.sync()
+elif what == "batched":
+    batch, m = int(sys.argv[2]), int(sys.argv[3])
+    a = np.random.default_rng(1).random((batch, m, m))
+    F = rfb200.lu_batched(a, ctx=ctx)

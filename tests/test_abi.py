@@ -57,12 +57,16 @@ def test_nsplit_matches_oracle(dtype):
 
 def test_argument_errors_are_loud():
     a = np.zeros((4, 4), order="F")
-    with pytest.raises(NotImplementedError):
-        rfb200.lu(a, False)
-    with pytest.raises(NotImplementedError):
-        rfb200.lu(a, rfb200.NoPivot())
     with pytest.raises(TypeError):
         rfb200.lu(a.astype(np.complex128))
+    with pytest.raises(TypeError):
+        rfb200.lu_(a, rfb200.NotIPIV(4), True)             # NotIPIV only with pivot = Val(false), src/lu.jl:33-40
+    with pytest.raises(ValueError):
+        rfb200.lu_(a, rfb200.NotIPIV(3), False)
+    with pytest.raises(TypeError):
+        rfb200.lu_batched_(np.zeros((2, 4, 4)))            # each matrix must be column-major
+    with pytest.raises(TypeError):
+        rfb200.ButterflyWorkspace(np.zeros((4, 5)), np.zeros(4))
     with pytest.raises(TypeError):
         rfb200.lu_(np.zeros((4, 4), order="C"))            # in-place needs column-major
     with pytest.raises(ValueError):
@@ -71,6 +75,18 @@ def test_argument_errors_are_loud():
         rfb200.lu_(a, np.zeros(4, dtype=np.int32))         # Vector{BlasInt} is int64
     with pytest.raises(TypeError):
         rfb200.lu(a, "yes")
+
+
+def test_notipiv_is_the_lazy_identity():
+    """src/lu.jl:27-32."""
+    p = rfb200.NotIPIV(5)
+    assert len(p) == 5 and p[0] == 1 and p[4] == 5 and list(p) == [1, 2, 3, 4, 5] and p == np.arange(1, 6)
+    F = rfb200.LU(np.asfortranarray(np.eye(5)), p, 0)
+    assert np.array_equal(F.p, np.arange(5))
+    with pytest.raises(rfb200.ZeroPivotException):
+        rfb200._checknonsingular(-3)
+    with pytest.raises(rfb200.SingularException):
+        rfb200._checknonsingular(3)
 
 
 def test_lu_object_properties():
