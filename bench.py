@@ -278,8 +278,17 @@ def run_ours(args, rank, world, local_rank):
             if it > 0:
                 et.append(dt)
         e_ms = max_over_ranks(1e3 * sum(et) / len(et))
+        # what was just timed must be a correct factorization too (this path uploads in column chunks, applies
+        # the interchanges eagerly and downloads finished rows early: a different schedule from the device path)
+        e_res = hutchinson_residual(host, np.asarray(hwork), ipiv_h)
+        checks["e2e_residual_fro_rel_est"] = e_res
+        checks["e2e_pivots_equal_device_path"] = bool(np.array_equal(ipiv_h, ipiv))
+        # raw PCIe rates of the same pinned buffers (explains e2e - device time; not part of any timed region)
+        t = time.perf_counter(); ctx.h2d(work.ptr, hwork); ctx.sync(); h2d_s = time.perf_counter() - t
+        t = time.perf_counter(); ctx.d2h(hwork, work.ptr); ctx.sync(); d2h_s = time.perf_counter() - t
         e2e = {"value": world * lu_flops(n) / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + n * 8 + 8}
+               "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + n * 8 + 8,
+               "pcie_h2d_GBps": n * n * 8 / h2d_s / 1e9, "pcie_d2h_GBps": n * n * 8 / d2h_s / 1e9}
 
     # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
     cpu = None

@@ -7,75 +7,114 @@
 // loop's own (multiply by the correctly rounded reciprocal, then one FMA per earlier column in
 // column order), so the result is bit-identical to that loop.
 //
-// B200 design: without a pivot search there is nothing to exchange between CTAs.  Every CTA
-// factors the n x n diagonal block REDUNDANTLY (n threads, one row each, kept in registers as the
-// same sliding window as K1) and publishes row k of U to shared memory at step k; the CTA's other
-// 128 threads each own one row below the diagonal block and eliminate it against that row in the
-// same step -- one __syncthreads per column, no grid-wide communication, no cooperative launch.
-// The panel is read once and written once (2*s*m*n bytes); the column of L produced at step k is
-// stored straight to global memory, coalesced down the column.
+// B200 design: without a pivot search there is nothing to exchange between CTAs.
+//   phase A -- every CTA factors the n x n diagonal block REDUNDANTLY in shared memory (256 threads,
+//              one __syncthreads per column; 32 KB read from L2), so no CTA waits for another one;
+//   phase B -- each of the CTA's 128 row threads owns one row below the diagonal block, loaded into
+//              registers BEFORE phase A so the HBM latency hides behind it, and eliminates it against
+//              the finished U with NO barrier at all: fully unrolled triangular loop, U values are
+//              shared-memory broadcasts, every update a register FMA.
+// The panel is read once and written once (2*s*m*n bytes).  (A first version published row k from the
+// registers of one thread at every step: 64 dependent STS per column on the critical path, 74 us per
+// 16384 x 64 panel -- profiles/r01_panel_nopiv_v1.txt.)
 #include "rfb_internal.h"
 
 namespace {
 
-constexpr int kRowThreads = 128;     // rows below the diagonal block per CTA
+constexpr int kNpThreads = 256;      // threads per CTA (phase A uses all of them)
+constexpr int kRowThreads = 128;     // rows below the diagonal block per CTA (phase B)
 
 __device__ __forceinline__ double rcp_rn(double v) { return __drcp_rn(v); }
 __device__ __forceinline__ float rcp_rn(float v) { return __frcp_rn(v); }
 
 template <typename T, int NB>
 struct NoPivShared {
-    T uw[NB][NB];      // uw[k][j] = U[k][k + j] (window-relative), zero beyond the panel width
-    T rinv[NB];        // 1 / U[k][k], or 1 when the pivot is exactly zero (column stays unscaled)
+    T d[NB][NB];       // diagonal block, row-major: d[i][j]; on exit of phase A row k holds U[k][k..] (j >= k)
+    T rinv[NB];        // 1 / U[k][k], or 1 when the pivot is exactly zero (column stays unscaled, :321-327)
     int first_zero;    // 1-based column of the first exactly-zero pivot, 0 = none
+    unsigned int ticket;
 };
 
 template <typename T, int NB>
-__global__ void __launch_bounds__(NB + kRowThreads)
+__global__ void __launch_bounds__(kNpThreads)
 panel_nopiv_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ info,
-                   long long col_offset) {
-    __shared__ NoPivShared<T, NB> sh;
+                   long long col_offset, unsigned int *__restrict__ loaded_counter) {
+    __shared__ __align__(16) NoPivShared<T, NB> sh;
     const int tid = threadIdx.x;
-    const bool diag = tid < NB;                                   // owns row `tid` of the diagonal block
-    const long long row = diag ? tid : (long long)n + (long long)blockIdx.x * kRowThreads + (tid - NB);
-    const bool have = diag ? (tid < n) : (row < m);
-    const bool writer = !diag || blockIdx.x == 0;                 // the diagonal block is written once
 
+    // phase B operands first: the loads are in flight while phase A runs
+    const long long row = (long long)n + (long long)blockIdx.x * kRowThreads + tid;
+    const bool have = tid < kRowThreads && row < m;
     T reg[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) reg[j] = (have && j < n) ? A[row + (long long)j * lda] : T(0);
-    if (tid == 0) sh.first_zero = 0;
-    bool alive = have;
 
+    // ---- phase A: unblocked LU of the diagonal block in shared memory ---------------------------
+    for (int e = tid; e < NB * NB; e += kNpThreads) {
+        const int i = e / NB, j = e % NB;
+        sh.d[i][j] = (i < n && j < n) ? A[i + (long long)j * lda] : T(0);
+    }
+    if (tid < NB) sh.rinv[tid] = T(1);
+    if (tid == 0) sh.first_zero = 0;
+    // The factored diagonal block goes back IN PLACE, but CTAs of a later wave may not have read the
+    // original yet: the CTA that is LAST to finish loading it (ticket == gridDim.x - 1) is the one
+    // that writes it, and it resets the counter for the next launch.  Nobody ever waits.
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        sh.ticket = atomicAdd(loaded_counter, 1u);
+    }
+    __syncthreads();
+    const bool writer = sh.ticket == gridDim.x - 1;
+    const int tx = tid % NB, ty = tid / NB;                      // column / row phase of this thread
+    constexpr int TY = kNpThreads / NB;
 #pragma unroll 1
     for (int k = 0; k < n; ++k) {
-        if (diag && tid == k) {                                   // row k of U is final: publish it
-            const T pv = reg[0];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) sh.uw[k][j] = reg[j];    // reg[j] == 0 beyond column n
-            sh.rinv[k] = (pv != T(0)) ? rcp_rn(pv) : T(1);        // :316-320 / :321-327
-            if (pv == T(0) && sh.first_zero == 0) sh.first_zero = k + 1;
-            if (writer) {
-                const int rem = n - k;
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if (j < rem) A[k + (long long)(k + j) * lda] = reg[j];
-            }
-            alive = false;
-        }
         __syncthreads();
-        if (alive) {
-            const T l = reg[0] * sh.rinv[k];
-            if (writer) A[row + (long long)k * lda] = l;
-            const T nl = -l;
-#pragma unroll
-            for (int j = 1; j < NB; ++j) reg[j - 1] = fma(nl, sh.uw[k][j], reg[j]);   // slide the window
-            reg[NB - 1] = T(0);
+        const T pv = sh.d[k][k];
+        const T r = (pv != T(0)) ? rcp_rn(pv) : T(1);            // :316-320
+        if (tid == 0) {
+            sh.rinv[k] = r;
+            if (pv == T(0) && sh.first_zero == 0) sh.first_zero = k + 1;
+        }
+        if (tx >= k && tx < n) {
+            const T ukj = sh.d[k][tx];
+#pragma unroll 4
+            for (int i = k + 1 + ty; i < n; i += TY) {
+                const T l = sh.d[i][k] * r;                      // column k itself is never rewritten in place
+                if (tx == k) {
+                    if (writer) A[i + (long long)k * lda] = l;   // L of the diagonal block
+                } else {
+                    sh.d[i][tx] = fma(-l, ukj, sh.d[i][tx]);     // :330-334
+                }
+            }
         }
     }
     __syncthreads();
-    if (blockIdx.x == 0 && tid == 0 && sh.first_zero != 0 && *info == 0)
-        *info = -(col_offset + sh.first_zero);                    // Julia >= 1.11: negative for NoPivot
+    if (writer) {                                                 // U of the diagonal block
+        for (int e = tid; e < n * n; e += kNpThreads) {
+            const int i = e % n, j = e / n;
+            if (j >= i) A[i + (long long)j * lda] = sh.d[i][j];
+        }
+        if (tid == 0) {
+            *loaded_counter = 0u;
+            if (sh.first_zero != 0 && *info == 0) *info = -(col_offset + sh.first_zero);   // Julia >= 1.11: negative
+        }
+    }
+
+    // ---- phase B: one row per thread against the finished U, no barriers ------------------------
+    if (!have) return;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const T l = reg[k] * sh.rinv[k];                          // columns >= n: 0 * 1
+        reg[k] = l;
+        const T nl = -l;
+#pragma unroll
+        for (int j = k + 1; j < NB; ++j) reg[j] = fma(nl, sh.d[k][j], reg[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+        if (j < n) A[row + (long long)j * lda] = reg[j];
 }
 
 template <typename T, int NB>
@@ -83,8 +122,8 @@ int launch_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *info, in
     const int rows_below = m - n;
     const int G = rows_below > 0 ? (rows_below + kRowThreads - 1) / kRowThreads : 1;
     RfbLaunchScope scope(ctx, RFB_KC_PANEL, (double)m * n * n - (double)n * n * n / 3.0);
-    panel_nopiv_kernel<T, NB><<<G, NB + kRowThreads, 0, ctx->stream>>>(A, m, n, (long long)lda, (long long *)info,
-                                                                     (long long)col_offset);
+    panel_nopiv_kernel<T, NB><<<G, kNpThreads, 0, ctx->stream>>>(A, m, n, (long long)lda, (long long *)info,
+                                                              (long long)col_offset, &ctx->xchg->pad[0]);
     RFB_CUDA(ctx, cudaGetLastError());
     return RFB_OK;
 }

@@ -31,9 +31,8 @@ struct LuPlan {
     // early download (host mode): rows [0, n1) of the root are final long before the factorization ends
     void *host_A = nullptr;            // caller's matrix (host), nullptr in device mode
     int64_t host_lda = 0, host_m = 0;
-    int64_t early_rows = 0;            // rows [0, early_rows) of columns [0, early_cols) were already sent back
-    int64_t early_cols = 0;
-    bool is_root_call = true;          // cleared while recursing below the root node
+    int64_t early_rows = 0;            // rows [0, early_rows) of ALL columns were already sent back (copy stream)
+    int64_t n_total = 0;               // columns of the whole matrix
     // pipelined upload (host mode): column chunk i is resident once up_events[i] has fired
     std::vector<cudaEvent_t> *up_events = nullptr;
     int64_t up_chunk = 0;  // columns per chunk
@@ -63,44 +62,59 @@ int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv,
 
 // reckernel! (src/lu.jl:189-263) on columns [c0, c0 + n) of the root matrix; the node's block is
 // rows [c0, m) (the diagonal block starts at row c0 == column c0).
+//
+// eager_left < 0: the reference's own order -- the interchanges of the right half reach the columns to
+//   their left when the node finishes (`apply_permutation!(P2, A21)`, :246).
+// eager_left >= 0 (pinned host matrices): every finished subtree of at most kEagerUnit columns applies its
+//   interchanges to ALL columns [eager_left, c0) on its left at once, so :246 has nothing left to do at the
+//   nodes above it.  Each column still receives every later pivot exactly once and in pivot order, so the
+//   result is identical; what changes is WHEN rows become final: after the swap + TRSM of a node on the
+//   right spine, rows [c0, c0 + n1) of every column are final and start travelling back to the host while
+//   the trailing update runs, instead of waiting for the end of the factorization.
+constexpr int64_t kEagerUnit = 512;
+constexpr int64_t kEarlyRowsMin = 1024;
+
 template <typename T>
 int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
-           LuPlan &plan) {
-    const bool at_root = plan.is_root_call;
-    plan.is_root_call = false;
+           LuPlan &plan, int64_t eager_left = -1) {
     T *A = root + c0 + c0 * lda;          // top-left of the node
     const int64_t mm = m - c0;            // rows of the node
+    if (eager_left >= 0 && n <= kEagerUnit) {
+        RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n, ipiv, info, plan, -1));
+        if (plan.pivot && c0 > eager_left)
+            RFB_TRY(lu_swap<T>(ctx, root + c0 + eager_left * lda, c0 - eager_left, lda, ipiv, c0, n, plan));
+        return RFB_OK;
+    }
     if (n <= plan.leaf) {                 // :192-195 leaf -> K1
         RFB_TRY(need_cols(ctx, plan, c0 + n));
         if (!plan.pivot) return rfb_launch_panel_nopiv<T>(ctx, A, mm, n, lda, info, c0);
         return rfb_launch_panel<T>(ctx, A, mm, n, lda, ipiv + c0, c0, info, c0, plan.lists ? c0 : -1);
     }
     const int64_t n1 = rfb_nsplit<T>(n), n2 = n - n1;                                   // :196-198
-    RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n1, ipiv, info, plan));                    // :229
+    RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n1, ipiv, info, plan, eager_left));        // :229
     T *AR = A + n1 * lda;
     RFB_TRY(need_cols(ctx, plan, c0 + n));
     if (plan.pivot) RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));          // :233
     RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
-    if (plan.host_A && at_root && n1 >= 1024) {
-        // root node, host mode: rows [0, n1) of ALL root columns (L11\U11 and U12) are final now -- the
-        // remaining steps only touch rows >= n1 -- so their download overlaps the trailing update.
+    if (plan.host_A && eager_left == 0 && c0 == plan.early_rows && c0 + n == plan.n_total && n1 >= kEarlyRowsMin) {
+        // right-spine node, pinned host matrix: rows [c0, c0 + n1) of ALL columns are final now (L and U11 on the
+        // left, U12 on the right; everything still to come touches rows >= c0 + n1 only).
         RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
         RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
-        RFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<T *>(plan.host_A), sizeof(T) * plan.host_lda, root, sizeof(T) * lda,
-                                        sizeof(T) * n1, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        plan.early_rows = n1;
-        plan.early_cols = n;
+        RFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<T *>(plan.host_A) + c0, sizeof(T) * plan.host_lda, root + c0,
+                                        sizeof(T) * lda, sizeof(T) * n1, plan.n_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        plan.early_rows = c0 + n1;
     }
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
-    RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan));               // :244
-    if (!plan.pivot) return RFB_OK;
+    RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan, eager_left));   // :244
+    if (!plan.pivot || eager_left >= 0) return RFB_OK;                                  // (eager: already applied)
     return lu_swap<T>(ctx, A + n1, n1, lda, ipiv, c0 + n1, n2, plan);                   // :246
 }
 
 template <typename T>
 int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d_ipiv, int64_t *d_info,
               const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, int64_t up_chunk = 0,
-              T *host_A = nullptr, int64_t host_lda = 0, int64_t *early_rows = nullptr, int64_t *early_cols = nullptr) {
+              T *host_A = nullptr, int64_t host_lda = 0, int64_t *early_rows = nullptr) {
     LuPlan plan;
     plan.opts = opts;
     plan.up_events = up_events;
@@ -108,6 +122,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     plan.host_A = host_A;
     plan.host_lda = host_lda;
     plan.host_m = m;
+    plan.n_total = n;
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     plan.pivot = !(opts && opts->no_pivot);
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
@@ -142,7 +157,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
         RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_dst, 0xFF, 2 * (size_t)mn * sizeof(int), ctx->stream));
         RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_width, 0, (size_t)mn * sizeof(int), ctx->stream));
     }
-    RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan));                   // :147
+    RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan, (host_A && m >= n) ? 0 : -1));   // :147
     if (m < n) {                                                                        // :148-154
         T *AR = dA + m * lda;
         RFB_TRY(need_cols(ctx, plan, n));
@@ -150,7 +165,6 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
     if (early_rows) *early_rows = plan.early_rows;
-    if (early_cols) *early_cols = plan.early_cols;
     return RFB_OK;
 }
 
@@ -487,21 +501,19 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
         RFB_CUDA(ctx, cudaEventRecord(ctx->up_events[c], ctx->copy_stream));
     }
     std::vector<cudaEvent_t> evs(ctx->up_events.begin(), ctx->up_events.begin() + nchunks);
-    int64_t early_rows = 0, early_cols = 0;
+    int64_t early_rows = 0;
     // the early download is only worth it (and only asynchronous) when the caller's matrix is page-locked
     cudaPointerAttributes pattr;
     const bool pinned = cudaPointerGetAttributes(&pattr, A) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, nopiv ? nullptr : ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols,
-                         (pinned && m >= n) ? A : nullptr, lda, &early_rows, &early_cols));
+                         (pinned && m >= n) ? A : nullptr, lda, &early_rows));
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
-    // download what the early copy (rows [0, early_rows) of the first early_cols columns) did not cover
+    // download what the early copies (rows [0, early_rows) of all columns) did not cover
     if (early_rows > 0) {
-        RFB_CUDA(ctx, cudaMemcpy2DAsync(A + early_rows, sizeof(T) * lda, dA + early_rows, sizeof(T) * ldd,
-                                        sizeof(T) * (m - early_rows), early_cols, cudaMemcpyDeviceToHost, ctx->stream));
-        if (early_cols < n)
-            RFB_CUDA(ctx, cudaMemcpy2DAsync(A + early_cols * lda, sizeof(T) * lda, dA + early_cols * ldd, sizeof(T) * ldd,
-                                            sizeof(T) * m, n - early_cols, cudaMemcpyDeviceToHost, ctx->stream));
+        if (early_rows < m)
+            RFB_CUDA(ctx, cudaMemcpy2DAsync(A + early_rows, sizeof(T) * lda, dA + early_rows, sizeof(T) * ldd,
+                                            sizeof(T) * (m - early_rows), n, cudaMemcpyDeviceToHost, ctx->stream));
         RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->copy_stream));
         RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));    // the early copy must be done before we return
     } else {

@@ -30,7 +30,7 @@ struct RfbPanelXchg {
     // row[parity][cta][j] = tagged { lo, hi } halves of the candidate row's value in window column j
     ulonglong2 row[2][RFB_MAX_PANEL_CTAS][RFB_MAX_NB];
     unsigned int error_flag;              // set by a kernel whose poll loop gave up
-    unsigned int pad[3];
+    unsigned int pad[3];                  // pad[0]: "diagonal block loaded" counter of the unpivoted panel kernel
 };
 
 enum RfbKernelClass { RFB_KC_PANEL = 0, RFB_KC_LASWP = 1, RFB_KC_TRSM = 2, RFB_KC_GEMM = 3, RFB_KC_OTHER = 4, RFB_KC_COUNT = 8 };
@@ -169,6 +169,10 @@ int rfb_launch_trsm_upper(rfb_ctx *ctx, const T *U, int64_t k, T *B, int64_t nrh
 template <typename T>
 int rfb_launch_gemm(rfb_ctx *ctx, T *C, const T *A, const T *B, int64_t m, int64_t n, int64_t k,
                     int64_t lda, const rfb_opts *opts);
+// K4 for n <= 8 right-hand-side columns (gemm_skinny.cu): HBM-bound GEMV-shaped update, deterministic
+constexpr int RFB_SKINNY_MAX_N = 8;
+template <typename T>
+int rfb_launch_gemm_skinny(rfb_ctx *ctx, T *C, const T *A, const T *B, int64_t m, int64_t n, int64_t k, int64_t lda);
 int rfb_launch_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);
 int rfb_run_dmma_peak(rfb_ctx *ctx, int iters, double *tflops);
 int rfb_run_copy_bench(rfb_ctx *ctx, size_t bytes, int iters, double *gbs);

@@ -12,8 +12,12 @@
 # and returns the same LinearAlgebra.LU{T,Matrix{T},Vector{BlasInt}} (src/lu.jl:129): the caller's
 # matrix mutated in place, the caller's pivot vector, info.  `thread`, `blocksize` and `threshold`
 # are accepted and ignored (they tune the CPU kernels); `leaf_width` is the GPU analogue.
-# Unsupported inputs (pivot = Val(false)/NoPivot(), complex or generic eltypes, non-strided
-# arrays) throw -- there is deliberately no CPU fallback.
+# pivot = Val(false) / NoPivot() (src/lu.jl:27-65) is supported: `NotIPIV` below is the reference's
+# lazy identity pivot vector, a user ipiv is filled with 1:min(m,n) (:107-113), info is negative on
+# a zero pivot (Julia >= 1.11, :24-25).  `🦋workspace` / `🦋solve!` (src/butterflylu.jl:20-55) and a
+# batched `lu_batched!` are bound further down.
+# Unsupported inputs (complex or generic eltypes, non-strided arrays) throw -- there is
+# deliberately no CPU fallback.
 module RecursiveFactorizationB200
 
 using LinearAlgebra
@@ -29,10 +33,19 @@ struct RfbOpts
     trsm_block::Int32
     gemm_path::Int32
     laswp_path::Int32
-    reserved::NTuple{10, Int32}
+    no_pivot::Int32
+    reserved::NTuple{9, Int32}
 end
-RfbOpts(; mem_space = 0, leaf_width = 0, f32_mode = 0, trsm_block = 0, gemm_path = 0, laswp_path = 0) =
-    RfbOpts(mem_space, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, ntuple(_ -> Int32(0), 10))
+RfbOpts(; mem_space = 0, leaf_width = 0, f32_mode = 0, trsm_block = 0, gemm_path = 0, laswp_path = 0, no_pivot = 0) =
+    RfbOpts(mem_space, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot, ntuple(_ -> Int32(0), 9))
+
+# src/lu.jl:27-32: the lazy identity pivot vector of an unpivoted factorization
+struct NotIPIV <: AbstractVector{BlasInt}
+    len::Int
+end
+Base.size(A::NotIPIV) = (A.len,)
+Base.getindex(::NotIPIV, i::Int) = i
+Base.view(::NotIPIV, r::AbstractUnitRange) = NotIPIV(length(r))
 
 mutable struct Context
     handle::Ptr{Cvoid}
@@ -69,14 +82,15 @@ _wants_check(::Val{true}) = true
 _wants_check(::Val{false}) = false
 
 for (T, sym) in ((Float64, :rfb_lu_f64), (Float32, :rfb_lu_f32))
-    @eval function _rfb_lu!(ctx::Context, A::StridedMatrix{$T}, ipiv::Vector{BlasInt}, opts::RfbOpts)
+    @eval function _rfb_lu!(ctx::Context, A::StridedMatrix{$T}, ipiv::Union{Vector{BlasInt}, NotIPIV}, opts::RfbOpts)
         m, n = size(A)
         stride(A, 1) == 1 || throw(ArgumentError("rfb200 needs unit row stride (column-major storage)"))
         info = Ref{Int64}(0)
         o = Ref(opts)
+        pp = ipiv isa NotIPIV ? Ptr{Int64}(C_NULL) : pointer(ipiv)          # NULL ipiv == NotIPIV (rfb200.h)
         rc = GC.@preserve A ipiv ccall(($(QuoteNode(sym)), librfb200), Cint,
             (Ptr{Cvoid}, Ptr{$T}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{RfbOpts}),
-            ctx.handle, pointer(A), m, n, max(1, stride(A, 2)), pointer(ipiv), info, o)
+            ctx.handle, pointer(A), m, n, max(1, stride(A, 2)), pp, info, o)
         rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
         return info[]
     end
@@ -86,19 +100,20 @@ function lu!(A::StridedMatrix{T}, ipiv::AbstractVector{<:Integer}, pivot = Val(t
         check::Union{Bool, Val{true}, Val{false}} = Val(true),
         blocksize::Integer = 0, threshold::Integer = 0,          # accepted, ignored (CPU knobs)
         leaf_width::Integer = 0, ctx::Context = default_context()) where {T <: Union{Float64, Float32}}
-    normalize_pivot(pivot) || throw(ArgumentError("pivot = Val(false)/NoPivot() is outside the B200 hot path"))
+    piv_on = normalize_pivot(pivot)
     BlasInt === Int64 || error("rfb200 writes Int64 pivots; this Julia has BlasInt = $BlasInt")
     length(ipiv) == min(size(A)...) || throw(DimensionMismatch("ipiv must have length min(m, n)"))
-    piv = ipiv isa Vector{BlasInt} ? ipiv : Vector{BlasInt}(undef, length(ipiv))
-    info = _rfb_lu!(ctx, A, piv, RfbOpts(leaf_width = leaf_width))
+    piv = (ipiv isa Vector{BlasInt} || ipiv isa NotIPIV) ? ipiv : Vector{BlasInt}(undef, length(ipiv))
+    info = _rfb_lu!(ctx, A, piv, RfbOpts(leaf_width = leaf_width, no_pivot = piv_on ? 0 : 1))
     piv === ipiv || copyto!(ipiv, piv)
-    _wants_check(check) && checknonsingular(info)                # SingularException, src/lu.jl:128
+    _wants_check(check) && checknonsingular(info)                # SingularException / ZeroPivotException, src/lu.jl:128
     return LU(A, ipiv, BlasInt(info))                            # src/lu.jl:129
 end
 
+# init_pivot, src/lu.jl:33-40
+init_pivot(piv_on::Bool, minmn) = piv_on ? Vector{BlasInt}(undef, minmn) : NotIPIV(minmn)
 function lu!(A::StridedMatrix{T}, pivot = Val(true), thread = Val(false); kwargs...) where {T <: Union{Float64, Float32}}
-    ipiv = Vector{BlasInt}(undef, min(size(A)...))               # init_pivot, src/lu.jl:40
-    return lu!(A, ipiv, pivot, thread; kwargs...)
+    return lu!(A, init_pivot(normalize_pivot(pivot), min(size(A)...)), pivot, thread; kwargs...)
 end
 
 lu(A::AbstractMatrix, pivot = Val(true), thread = Val(false); kwargs...) =
@@ -121,6 +136,67 @@ function ldiv_gpu!(F::LU{Float64, <:StridedMatrix{Float64}, <:Vector{BlasInt}}, 
         B isa AbstractVector ? n : stride(B, 2), o)
     rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
     return B
+end
+
+# ldiv!(F::LU{T,<:StridedMatrix,<:NotIPIV}, B) (src/lu.jl:60-64): two triangular solves, no interchanges
+function LinearAlgebra.ldiv!(F::LU{Float64, <:StridedMatrix{Float64}, <:NotIPIV}, B::StridedVecOrMat{Float64};
+        ctx::Context = default_context())
+    n = size(F.factors, 1)
+    o = Ref(RfbOpts())
+    rc = GC.@preserve F B ccall((:rfb_solve_f64, librfb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Ptr{RfbOpts}),
+        ctx.handle, pointer(F.factors), n, stride(F.factors, 2), C_NULL, pointer(B), size(B, 2),
+        B isa AbstractVector ? n : stride(B, 2), o)
+    rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+    return B
+end
+
+# ---------------------------------------------------------------------------------------------
+# 🦋 (src/butterflylu.jl:20-57).  The workspace keeps the caller's A and b; padding (pad!, :180-197),
+# the transform (🦋mul!, :93-113), the unpivoted LU and both butterfly matrix-vector products run
+# inside one library call.  `ws` holds the 4n butterfly values (generate_rand_butterfly_vals!, :7-13,
+# drawn here from Julia's default RNG: the reference's VectorizedRNG stream is SIMD-width dependent).
+# ---------------------------------------------------------------------------------------------
+struct 🦋workspace{T}
+    A::Matrix{T}
+    b::Vector{T}
+    ws::Vector{T}
+    out::Vector{T}
+    n::Int
+    function 🦋workspace(A::Matrix{T}, b::Vector{T}) where {T <: Union{Float64, Float32}}
+        n = size(A, 1)
+        np = n % 4 == 0 ? n : n + (4 - n % 4)
+        ws = T.(exp.(T(-0.05) .+ T(0.1) .* rand(T, 4np)) .* T(0.5))
+        new{T}(A, b, ws, similar(b), n)
+    end
+end
+const butterfly_workspace = 🦋workspace
+
+function 🦋solve!(w::🦋workspace{Float64}, thread = Val(false); ctx::Context = default_context())
+    copyto!(w.out, w.b)
+    info = Ref{Int64}(0)
+    o = Ref(RfbOpts())
+    rc = GC.@preserve w ccall((:rfb_butterfly_solve_f64, librfb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{RfbOpts}),
+        ctx.handle, pointer(w.A), w.n, stride(w.A, 2), pointer(w.out), 1, w.n, pointer(w.ws), info, o)
+    rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+    checknonsingular(info[])                                     # lu!(A, Val(false), thread) checks (:48)
+    return w.out
+end
+
+# lu! over the slices A[:, :, b] of a 3-D array (one launch when n <= 64 and m <= 128)
+function lu_batched!(A::Array{Float64, 3}; check = true, ctx::Context = default_context())
+    m, n, batch = size(A)
+    mn = min(m, n)
+    ipiv = Matrix{BlasInt}(undef, mn, batch)
+    info = Vector{Int64}(undef, batch)
+    o = Ref(RfbOpts())
+    rc = GC.@preserve A ipiv info ccall((:rfb_lu_batched_f64, librfb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{RfbOpts}),
+        ctx.handle, pointer(A), m, n, max(1, m), m * n, batch, pointer(ipiv), pointer(info), o)
+    rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+    check && foreach(checknonsingular, info)
+    return [LU(view(A, :, :, b), view(ipiv, :, b), BlasInt(info[b])) for b in 1:batch]
 end
 
 # everything else is not on the GPU path: fail loudly instead of silently running on the CPU

@@ -61,6 +61,15 @@ for n in (4096, 16384):
     t = timed(solve, reps=3, pre=pre)
     out[f"butterfly_solve_f64_{n}_device"] = {"ms": round(t, 3), "gflops_lu_equiv": round(2 * n ** 3 / 3 / t / 1e6, 1)}
     print("butterfly_solve", n, out[f"butterfly_solve_f64_{n}_device"], flush=True)
+    # ---- ldiv!(F, B) on the factors just produced: vector and block right-hand sides ------------------
+    for nrhs in (1, 4, 64, 1024):
+        bb = ctx.malloc(n * nrhs * 8); ctx.memset(bb, 0, n * nrhs * 8)
+        run = lambda: ctx._check(lib.rfb_solve_f64(h, C.c_void_p(dst.ptr), n, n, None, C.c_void_p(bb), nrhs, n, C.byref(opts)))
+        t = timed(run, reps=3)
+        out[f"ldiv_notipiv_f64_{n}_nrhs{nrhs}"] = {"ms": round(t, 3), "GBps_factors": round(8.0 * n * n / t / 1e6, 1),
+                                                   "gflops": round(2.0 * n * n * nrhs / t / 1e6, 1)}
+        print("ldiv", n, nrhs, out[f"ldiv_notipiv_f64_{n}_nrhs{nrhs}"], flush=True)
+        ctx.free(bb)
     ctx.free(duv); ctx.free(b); ctx.free(info); src.free(); dst.free()
 
 # ---- butterfly solve end to end from host (n = 8192) vs pivoted lu + solve --------------------------------

@@ -189,19 +189,28 @@ def test_baseline_config_f32_8192_tensor_core(ctx):
     assert res <= 20 * n * np.finfo(np.float32).eps, res
 
 
-def test_pinned_host_matrix_early_download(ctx):
-    """Page-locked caller matrix: the upload is pipelined and rows [0, n1) of the root are downloaded
-    while the trailing update still runs; the result must be identical to the pageable-path result."""
-    n = 4096
-    a0 = np.asfortranarray(np.random.default_rng(77).random((n, n)))
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (4096, 4096)), (np.float64, (3000, 3000)), (np.float64, (5000, 2500)),
+                                         (np.float32, (4100, 4100)), (np.float64, (2048, 2600)), (np.float64, (1500, 1500))])
+def test_pinned_host_matrix_early_download(ctx, dtype, shape):
+    """Page-locked caller matrix: the upload is pipelined, finished subtrees apply their interchanges to all
+    columns on their left at once (instead of at the end of each node, src/lu.jl:246), and the rows of every
+    right-spine node travel back to the host while its trailing update still runs.  Same swaps in the same
+    per-column order: the result must be IDENTICAL to the pageable-path result (reference order)."""
+    m, n = shape
+    a0 = rand_matrix(np.random.default_rng([77, m, n]), m, n, dtype)
     F_ref = rfb200.lu(a0, ctx=ctx)                       # pageable numpy memory
-    a_pin = ctx.pinned_empty((n, n), np.float64)
+    a_pin = ctx.pinned_empty((m, n), dtype)
     np.copyto(a_pin, a0)
-    ipiv = np.empty(n, dtype=np.int64)
+    ipiv = np.empty(min(m, n), dtype=np.int64)
     F = rfb200.lu_(a_pin, ipiv, ctx=ctx)
     assert F.info == 0
     assert np.array_equal(F.ipiv, F_ref.ipiv)
     assert np.array_equal(np.asarray(F.factors), F_ref.factors)
+    # and without pivoting (no interchanges to move, downloads only)
+    G_ref = rfb200.lu(a0 + 10 * np.eye(m, n, dtype=dtype), False, ctx=ctx)
+    np.copyto(a_pin, a0 + 10 * np.eye(m, n, dtype=dtype))
+    G = rfb200.lu_(a_pin, None, False, ctx=ctx)
+    assert np.array_equal(np.asarray(G.factors), G_ref.factors)
 
 
 @pytest.mark.parametrize("shape", [(50000, 48), (90000, 24), (40000, 200)])
