@@ -114,7 +114,8 @@ __device__ __forceinline__ Cand block_best(Cand c, ReduceBuf<WARPS> &buf, int wa
 template <typename T, int NB, int WARPS>
 struct PanelShared {
     T u[2][NB];
-    T pub[NB];          // staging of the CTA winner's row window for the warp-wide publish
+    T rinv[2];          // reciprocal of the pivot (1 for an exactly-zero pivot), computed by the winner
+    T pub[NB + 1];      // staging of the CTA winner's row window (+ its reciprocal) for the warp-wide publish
     ReduceBuf<WARPS> loc[2];
     ReduceBuf<WARPS> glb[2];
 };
@@ -182,6 +183,10 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
 
         // -- local candidate (src/lu.jl:296-305) ------------------------------------------------
         const T av = fabs(reg[0]);
+        // Every candidate computes the reciprocal of ITS OWN value now: the ~7 dependent FP64 operations of
+        // the correctly rounded reciprocal run in the shadow of the reduction / exchange below instead of
+        // on the critical path after it (the winner's value is the one that gets used, :317-320).
+        const T myrinv = (reg[0] != T(0)) ? rcp_rn(reg[0]) : T(1);
         Cand c;
         c.key = (alive && av > T(0)) ? to_bits(av) : 0ull;
         c.lp = alive ? logpos : kNone;
@@ -195,6 +200,9 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
             if (cta_winner) {
 #pragma unroll
                 for (int j = 0; j < NB; ++j) sh.u[par][j] = reg[j];
+                sh.rinv[par] = myrinv;
+            } else if (cb.lp == kNone && tid == 0) {
+                sh.rinv[par] = T(1);                  // no candidate at all (zeros / NaNs only): u stays as it is
             }
             __syncthreads();
         } else {
@@ -204,6 +212,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                 st_tagged(&x->header[par][bid].h[1], epoch, cb.lp, 0u);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) sh.pub[j] = reg[j];
+                sh.pub[NB] = myrinv;
             } else if (cb.lp == kNone && tid == 0) {
                 st_tagged(&x->header[par][bid].h[0], epoch, 0u, 0u);
                 st_tagged(&x->header[par][bid].h[1], epoch, kNone, 0u);
@@ -216,6 +225,10 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                         const unsigned long long bits = to_bits(sh.pub[j]);
                         st_tagged(&x->row[par][bid][j], epoch, (unsigned int)bits, (unsigned int)(bits >> 32));
                     }
+                if (lane == 0) {
+                    const unsigned long long bits = to_bits(sh.pub[NB]);
+                    st_tagged(&x->row[par][bid][RFB_MAX_NB], epoch, (unsigned int)bits, (unsigned int)(bits >> 32));
+                }
             }
             // -- gather all G headers, reduce redundantly in every CTA --------------------------
             Cand g{0ull, kNone, 0u};
@@ -255,6 +268,23 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                     val = from_bits<T>(((unsigned long long)vhi << 32) | vlo);
                 }
                 sh.u[par][tid] = val;
+            } else if (tid == NB) {                   // one more thread fetches the winner's reciprocal
+                T val = T(1);
+                if (wb.lp != kNone) {
+                    unsigned int vlo, vhi;
+                    unsigned int spins = 0;
+                    while (true) {
+                        if (ld_tagged(&x->row[par][wb.src][RFB_MAX_NB], epoch, vlo, vhi)) break;
+                        if (bailed) break;
+                        if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_flag(&x->error_flag))) {
+                            atomicExch(&x->error_flag, 1u);
+                            bailed = true;
+                            break;
+                        }
+                    }
+                    val = from_bits<T>(((unsigned long long)vhi << 32) | vlo);
+                }
+                sh.rinv[par] = val;
             }
             __syncthreads();
         }
@@ -270,7 +300,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         } else if (alive) {
             if (logpos == (unsigned int)k) { logpos = wb.lp; dslot = k; }   // the swap k <-> kp, on the index
             T l = reg[0];
-            if (pv != T(0)) l *= rcp_rn(pv);                 // reciprocal scaling (:317-320)
+            if (pv != T(0)) l *= sh.rinv[par];               // reciprocal scaling (:317-320)
             fin[k * THREADS + tid] = l;
             const T nl = -l;
 #pragma unroll

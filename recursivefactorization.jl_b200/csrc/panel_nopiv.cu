@@ -63,6 +63,9 @@ panel_nopiv_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__
     if (tid == 0) {
         __threadfence();
         sh.ticket = atomicAdd(loaded_counter, 1u);
+        const T p0 = sh.d[0][0];
+        sh.rinv[0] = (p0 != T(0)) ? rcp_rn(p0) : T(1);           // :316-320
+        if (p0 == T(0)) sh.first_zero = 1;
     }
     __syncthreads();
     const bool writer = sh.ticket == gridDim.x - 1;
@@ -71,16 +74,19 @@ panel_nopiv_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__
 #pragma unroll 1
     for (int k = 0; k < n; ++k) {
         __syncthreads();
-        const T pv = sh.d[k][k];
-        const T r = (pv != T(0)) ? rcp_rn(pv) : T(1);            // :316-320
-        if (tid == 0) {
-            sh.rinv[k] = r;
-            if (pv == T(0) && sh.first_zero == 0) sh.first_zero = k + 1;
-        }
+        const T r = sh.rinv[k];
         if (tx >= k && tx < n) {
             const T ukj = sh.d[k][tx];
+            if (tx == k + 1 && ty == 0) {
+                // this thread produces the NEXT pivot first and computes its correctly rounded reciprocal at
+                // once, so those ~7 dependent FP64 operations overlap the other threads' updates of this step
+                const T nd = fma(-(sh.d[k + 1][k] * r), ukj, sh.d[k + 1][tx]);
+                sh.d[k + 1][tx] = nd;
+                sh.rinv[k + 1] = (nd != T(0)) ? rcp_rn(nd) : T(1);
+                if (nd == T(0) && sh.first_zero == 0) sh.first_zero = k + 2;
+            }
 #pragma unroll 4
-            for (int i = k + 1 + ty; i < n; i += TY) {
+            for (int i = k + 1 + ty + ((tx == k + 1 && ty == 0) ? TY : 0); i < n; i += TY) {
                 const T l = sh.d[i][k] * r;                      // column k itself is never rewritten in place
                 if (tx == k) {
                     if (writer) A[i + (long long)k * lda] = l;   // L of the diagonal block

@@ -28,7 +28,8 @@ struct RfbPanelXchg {
     // header[parity][cta].h = tagged { |candidate| bits lo, hi } and { logical row, 0 }
     RfbPanelHeader header[2][RFB_MAX_PANEL_CTAS];
     // row[parity][cta][j] = tagged { lo, hi } halves of the candidate row's value in window column j
-    ulonglong2 row[2][RFB_MAX_PANEL_CTAS][RFB_MAX_NB];
+    // slot [RFB_MAX_NB] carries the reciprocal of the candidate's own value (the pivot's, if it wins)
+    ulonglong2 row[2][RFB_MAX_PANEL_CTAS][RFB_MAX_NB + 2];
     unsigned int error_flag;              // set by a kernel whose poll loop gave up
     unsigned int pad[3];                  // pad[0]: "diagonal block loaded" counter of the unpivoted panel kernel
 };
