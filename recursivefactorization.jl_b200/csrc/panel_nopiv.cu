@@ -75,32 +75,31 @@ panel_nopiv_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__
     for (int k = 0; k < n; ++k) {
         __syncthreads();
         const T r = sh.rinv[k];
-        if (tx >= k && tx < n) {
+        // Branch-free trailing update of columns tx > k.  Column k itself is never rewritten in place: after
+        // the loop d[i][k] (i > k) still holds the value the unblocked loop would scale at step k, so L is
+        // formed once at the end as d[i][k] * rinv[k] -- the same product, bit for bit.  (Storing L from
+        // inside this loop made it divergent and 6x slower: profiles/r01_panel_nopiv_v2.txt.)
+        if (tx > k && tx < n) {
             const T ukj = sh.d[k][tx];
+            int i = k + 1 + ty;
             if (tx == k + 1 && ty == 0) {
                 // this thread produces the NEXT pivot first and computes its correctly rounded reciprocal at
-                // once, so those ~7 dependent FP64 operations overlap the other threads' updates of this step
+                // once, so that dependent chain overlaps the other threads' updates of this step
                 const T nd = fma(-(sh.d[k + 1][k] * r), ukj, sh.d[k + 1][tx]);
                 sh.d[k + 1][tx] = nd;
-                sh.rinv[k + 1] = (nd != T(0)) ? rcp_rn(nd) : T(1);
+                sh.rinv[k + 1] = (nd != T(0)) ? rcp_rn(nd) : T(1);   // :316-320
                 if (nd == T(0) && sh.first_zero == 0) sh.first_zero = k + 2;
+                i += TY;
             }
 #pragma unroll 4
-            for (int i = k + 1 + ty + ((tx == k + 1 && ty == 0) ? TY : 0); i < n; i += TY) {
-                const T l = sh.d[i][k] * r;                      // column k itself is never rewritten in place
-                if (tx == k) {
-                    if (writer) A[i + (long long)k * lda] = l;   // L of the diagonal block
-                } else {
-                    sh.d[i][tx] = fma(-l, ukj, sh.d[i][tx]);     // :330-334
-                }
-            }
+            for (; i < n; i += TY) sh.d[i][tx] = fma(-(sh.d[i][k] * r), ukj, sh.d[i][tx]);   // :330-334
         }
     }
     __syncthreads();
-    if (writer) {                                                 // U of the diagonal block
+    if (writer) {                                                 // L\U of the diagonal block, written once
         for (int e = tid; e < n * n; e += kNpThreads) {
             const int i = e % n, j = e / n;
-            if (j >= i) A[i + (long long)j * lda] = sh.d[i][j];
+            A[i + (long long)j * lda] = (j >= i) ? sh.d[i][j] : sh.d[i][j] * sh.rinv[j];
         }
         if (tid == 0) {
             *loaded_counter = 0u;
