@@ -120,6 +120,16 @@ struct PanelShared {
     ReduceBuf<WARPS> glb[2];
 };
 
+// One CTA's candidate of one step in the cluster (DSMEM) exchange.
+template <typename T, int NB>
+struct ClusterSlot {
+    unsigned long long key;
+    unsigned int lp;
+    unsigned int pad;
+    T rinv;
+    T row[NB];
+};
+
 // Row-exchange list of one panel (consumed by the list-driven laswp, laswp.cu): which rows of the
 // panel changed place.  Slot k < n: pivot row k (dst = row0 + k).  Slot n + k: the row that the
 // k-th interchange displaced and that still sits there at the end.  Unused slots keep dst = -1
@@ -143,7 +153,14 @@ struct PanelPermOut {
 // reference's own small-matrix path is this unblocked loop, src/lu.jl:125-126): one CTA per matrix
 // (blockIdx.x = matrix, up to THREADS rows and NB columns, fat shapes included -- the loop runs
 // min(m, n) pivot steps over all n columns), no inter-CTA exchange.
-template <typename T, int NB, int THREADS, bool BATCHED = false>
+//
+// CLUSTER = true: the whole panel (up to 16 x THREADS rows) is ONE thread-block cluster and the per-column
+// exchange goes through DISTRIBUTED SHARED MEMORY instead of L2: each CTA's winner leaves {key, row, 1/pivot}
+// in its own shared-memory slot, one barrier.cluster (~380 cycles) makes all slots visible, every CTA reads
+// the <= 16 headers remotely (~215 cycles), reduces, and reads the winning row remotely.  That replaces three
+// dependent L2 round trips (~700 cycles each on this part) per column; two slot parities make the slots
+// reusable with that single cluster barrier per column.
+template <typename T, int NB, int THREADS, bool BATCHED = false, bool CLUSTER = false>
 __global__ void __launch_bounds__(THREADS, 1)
 panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restrict__ ipiv,
              long long ipiv_add, long long *__restrict__ info, long long col_offset,
@@ -153,6 +170,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
     extern __shared__ __align__(16) unsigned char panel_smem[];
     T *fin = reinterpret_cast<T *>(panel_smem);                 // [NB][THREADS]
     __shared__ PanelShared<T, NB, WARPS> sh;
+    __shared__ ClusterSlot<T, NB> cslot[CLUSTER ? 2 : 1];       // this CTA's candidate, read remotely by the cluster
 
     const int G = BATCHED ? 1 : (int)gridDim.x, bid = BATCHED ? 0 : (int)blockIdx.x, tid = threadIdx.x;
     if (BATCHED) {
@@ -195,7 +213,34 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         const bool cta_winner = alive && logpos == cb.lp;
 
         Cand wb;
-        if (G == 1) {
+        if (CLUSTER) {
+            namespace cg = cooperative_groups;
+            cg::cluster_group cluster = cg::this_cluster();
+            ClusterSlot<T, NB> &mine = cslot[CLUSTER ? par : 0];
+            if (cta_winner) {
+                mine.key = cb.key;
+                mine.lp = cb.lp;
+                mine.rinv = myrinv;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) mine.row[j] = reg[j];
+            } else if (cb.lp == kNone && tid == 0) {
+                mine.key = 0ull;
+                mine.lp = kNone;
+            }
+            cluster.sync();                                   // every CTA's slot of this parity is complete and visible
+            Cand g{0ull, kNone, 0u};
+            if (tid < G) {
+                const ClusterSlot<T, NB> *rs = cluster.map_shared_rank(&mine, tid);
+                g.key = rs->key;
+                g.lp = rs->lp;
+                g.src = (unsigned int)tid;
+            }
+            wb = block_best<WARPS>(g, sh.glb[par], warp, lane);
+            const ClusterSlot<T, NB> *ws = cluster.map_shared_rank(&mine, wb.src);
+            if (tid < NB) sh.u[par][tid] = ws->row[tid];
+            else if (tid == NB) sh.rinv[par] = ws->rinv;
+            __syncthreads();
+        } else if (G == 1) {
             wb = cb;
             if (cta_winner) {
 #pragma unroll
@@ -328,6 +373,7 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         }
     }
     if (perm.width != nullptr && bid == 0 && tid == 0) perm.width[0] = n;
+    if (CLUSTER) cooperative_groups::this_cluster().sync();     // nobody may exit while its slots can still be read
 }
 
 #ifdef RFB_PANEL_BATCHED
@@ -416,6 +462,58 @@ int launch_panel_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ip
     return RFB_OK;
 }
 
+// Single-cluster launch (DSMEM exchange): G <= 16 CTAs of 256 threads.  *handled = false when this device /
+// driver cannot co-schedule such a cluster (the caller then uses the L2 exchange).
+template <typename T, int NB>
+int launch_panel_cluster_inst(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
+                              int64_t *info, int64_t col_offset, int G, PanelPermOut perm, bool *handled) {
+    constexpr int THREADS = 256;
+    auto kern = panel_kernel<T, NB, THREADS, false, true>;
+    constexpr size_t smem = sizeof(T) * NB * THREADS;
+    *handled = false;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const auto key = std::make_pair((const void *)kern, G);
+    auto it = ctx->cluster_ok.find(key);
+    if (it == ctx->cluster_ok.end()) {
+        bool ok = true;
+        if (G > 8 && cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
+        int nclusters = 0;
+        if (ok && (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)kern, &cfg) != cudaSuccess || nclusters < 1)) ok = false;
+        cudaGetLastError();
+        it = ctx->cluster_ok.emplace(key, ok).first;
+    }
+    if (!it->second) return RFB_OK;
+    long long lda_ = lda, add_ = ipiv_add, off_ = col_offset, zero_ = 0;
+    long long *ipiv_ = (long long *)ipiv, *info_ = (long long *)info;
+    RfbPanelXchg *x = ctx->xchg;
+    unsigned int epoch = 0;
+    void *args[] = {&A, &m, &n, &lda_, &ipiv_, &add_, &info_, &off_, &x, &epoch, &perm, &zero_, &zero_};
+    RfbLaunchScope scope(ctx, RFB_KC_PANEL, (double)m * n * n - (double)n * n * n / 3.0);
+    RFB_CUDA(ctx, cudaLaunchKernelExC(&cfg, (const void *)kern, args));
+    *handled = true;
+    return RFB_OK;
+}
+
+template <typename T>
+int launch_panel_cluster(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add, int64_t *info,
+                         int64_t col_offset, int G, PanelPermOut perm, bool *handled) {
+    if (n <= 16) return launch_panel_cluster_inst<T, 16>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G, perm, handled);
+    if (n <= 32) return launch_panel_cluster_inst<T, 32>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G, perm, handled);
+    return launch_panel_cluster_inst<T, 64>(ctx, A, m, n, lda, ipiv, ipiv_add, info, col_offset, G, perm, handled);
+}
+
 template <typename T, int THREADS>
 int launch_panel_threads(rfb_ctx *ctx, T *A, int m, int n, int64_t lda, int64_t *ipiv, int64_t ipiv_add,
                          int64_t *info, int64_t col_offset, int G, PanelPermOut perm) {
@@ -449,6 +547,20 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
     static const int force_threads = getenv("RFB_PANEL_THREADS") ? atoi(getenv("RFB_PANEL_THREADS")) : 0;   // tuning aid
     // 128-thread CTAs spread over more SMs; the wide (64-column) kernel fits one 256-thread CTA per SM,
     // which is what lets a 64-column panel reach 148 x 256 rows; narrower panels fit several CTAs per SM
+    static const int use_cluster = getenv("RFB_PANEL_CLUSTER") ? atoi(getenv("RFB_PANEL_CLUSTER")) : 1;   // A/B switch
+    if (g256 == 1 && m > 128 && force_threads != 128) {
+        // up to 256 rows: one 256-thread CTA, no inter-CTA exchange at all
+        rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, 1, perm);
+        if (rc != RFB_OK) return rc;
+        ctx->panel_epoch += (unsigned int)n;
+        return rc;
+    }
+    if (use_cluster && g256 >= 2 && g256 <= 16 && force_threads == 0) {
+        // up to 4096 rows: one thread-block cluster, exchange through distributed shared memory
+        bool handled = false;
+        RFB_TRY(launch_panel_cluster<T>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g256, perm, &handled));
+        if (handled) return RFB_OK;
+    }
     int cap128 = n <= 16 ? panel_capacity<T, 16, 128>(ctx) : n <= 32 ? panel_capacity<T, 32, 128>(ctx) : panel_capacity<T, 64, 128>(ctx);
     if (g128 <= cap128 && force_threads != 256)
         rc = launch_panel_threads<T, 128>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, (int)g128, perm);

@@ -77,6 +77,8 @@ struct rfb_ctx {
 
     // co-resident CTA capacity of each panel-kernel instantiation (cooperative launch limit)
     std::map<const void *, int> panel_capacity;
+    // (kernel, cluster size) -> can this device co-schedule one such cluster (DSMEM panel exchange)
+    std::map<std::pair<const void *, int>, bool> cluster_ok;
     // kernels whose dynamic shared memory limit has been raised on this device
     std::set<const void *> smem_configured;
 
