@@ -113,7 +113,7 @@ __device__ __forceinline__ Cand block_best(Cand c, ReduceBuf<WARPS> &buf, int wa
 
 template <typename T, int NB, int WARPS>
 struct PanelShared {
-    T u[2][NB];
+    alignas(16) T u[2][NB];
     T rinv[2];          // reciprocal of the pivot (1 for an exactly-zero pivot), computed by the winner
     T pub[NB + 1];      // staging of the CTA winner's row window (+ its reciprocal) for the warp-wide publish
     ReduceBuf<WARPS> loc[2];
@@ -222,7 +222,11 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                 mine.lp = cb.lp;
                 mine.rinv = myrinv;
 #pragma unroll
-                for (int j = 0; j < NB; ++j) mine.row[j] = reg[j];
+                for (int c8 = 0; c8 < NB; c8 += 8)
+                    if (c8 <= rem) {
+#pragma unroll
+                        for (int j = c8; j < c8 + 8; ++j) mine.row[j] = reg[j];
+                    }
             } else if (cb.lp == kNone && tid == 0) {
                 mine.key = 0ull;
                 mine.lp = kNone;
@@ -244,7 +248,11 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
             wb = cb;
             if (cta_winner) {
 #pragma unroll
-                for (int j = 0; j < NB; ++j) sh.u[par][j] = reg[j];
+                for (int c8 = 0; c8 < NB; c8 += 8)
+                    if (c8 <= rem) {
+#pragma unroll
+                        for (int j = c8; j < c8 + 8; ++j) sh.u[par][j] = reg[j];
+                    }
                 sh.rinv[par] = myrinv;
             } else if (cb.lp == kNone && tid == 0) {
                 sh.rinv[par] = T(1);                  // no candidate at all (zeros / NaNs only): u stays as it is
@@ -256,7 +264,11 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                 st_tagged(&x->header[par][bid].h[0], epoch, (unsigned int)cb.key, (unsigned int)(cb.key >> 32));
                 st_tagged(&x->header[par][bid].h[1], epoch, cb.lp, 0u);
 #pragma unroll
-                for (int j = 0; j < NB; ++j) sh.pub[j] = reg[j];
+                for (int c8 = 0; c8 < NB; c8 += 8)
+                    if (c8 < rem) {
+#pragma unroll
+                        for (int j = c8; j < c8 + 8; ++j) sh.pub[j] = reg[j];
+                    }
                 sh.pub[NB] = myrinv;
             } else if (cb.lp == kNone && tid == 0) {
                 st_tagged(&x->header[par][bid].h[0], epoch, 0u, 0u);
@@ -340,16 +352,26 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
             alive = false;            // this row is pivot row k: frozen; its window is row k of U
             finalpos = k;
 #pragma unroll
-            for (int j = 0; j < NB; ++j)
-                if (j < rem) fin[(k + j) * THREADS + tid] = reg[j];
+            for (int c8 = 0; c8 < NB; c8 += 8)
+                if (c8 < rem) {
+#pragma unroll
+                    for (int j = c8; j < c8 + 8; ++j)
+                        if (j < rem) fin[(k + j) * THREADS + tid] = reg[j];
+                }
         } else if (alive) {
             if (logpos == (unsigned int)k) { logpos = wb.lp; dslot = k; }   // the swap k <-> kp, on the index
             T l = reg[0];
             if (pv != T(0)) l *= sh.rinv[par];               // reciprocal scaling (:317-320)
             fin[k * THREADS + tid] = l;
             const T nl = -l;
+            // slide the window, in chunks of 8 columns; a chunk runs iff it still holds live columns (8c <= rem:
+            // warp-uniform, and the publisher wrote exactly the same chunks, zeros beyond the live width)
 #pragma unroll
-            for (int j = 1; j < NB; ++j) reg[j - 1] = fma(nl, sh.u[par][j], reg[j]);   // slide the window
+            for (int c8 = 0; c8 < NB; c8 += 8)
+                if (c8 <= rem) {
+#pragma unroll
+                    for (int j = (c8 == 0 ? 1 : c8); j < c8 + 8; ++j) reg[j - 1] = fma(nl, sh.u[par][j], reg[j]);
+                }
             reg[NB - 1] = T(0);
         }
         if (bid == 0 && tid == 0) {
@@ -547,7 +569,10 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
     static const int force_threads = getenv("RFB_PANEL_THREADS") ? atoi(getenv("RFB_PANEL_THREADS")) : 0;   // tuning aid
     // 128-thread CTAs spread over more SMs; the wide (64-column) kernel fits one 256-thread CTA per SM,
     // which is what lets a 64-column panel reach 148 x 256 rows; narrower panels fit several CTAs per SM
-    static const int use_cluster = getenv("RFB_PANEL_CLUSTER") ? atoi(getenv("RFB_PANEL_CLUSTER")) : 1;   // A/B switch
+    // A/B switch, default OFF: measured on B200 (run 15, profiles/r01_panel_cluster_m4096.txt) the DSMEM exchange is
+    // no faster than the L2 one (2.09 vs 2.08 us per column at 4096 rows, 1.95 vs 1.80 at 512): a column costs
+    // ~4000 cycles spread evenly over the in-CTA stages (reduce, publish, fetch, eliminate), not the medium.
+    static const int use_cluster = getenv("RFB_PANEL_CLUSTER") ? atoi(getenv("RFB_PANEL_CLUSTER")) : 0;
     if (g256 == 1 && m > 128 && force_threads != 128) {
         // up to 256 rows: one 256-thread CTA, no inter-CTA exchange at all
         rc = launch_panel_threads<T, 256>(ctx, A, (int)m, (int)n, lda, ipiv_dev, ipiv_add, info_dev, col_offset, 1, perm);
