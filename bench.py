@@ -167,6 +167,69 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def other_configs(ctx, rfb200):
+    """Device-resident timings (CUDA events, best of 3 after a warm-up, matrix restored by an untimed copy) of the
+    other single-GPU BASELINE.json configs and of the rows SURVEY.md section 8f widens into.  Informational: the
+    headline `value` / `e2e` above are the 16384 x 16384 Float64 pivoted LU."""
+    import ctypes as C
+    out = {}
+
+    def timed(fn, pre, reps=3):
+        best = None
+        for i in range(reps + 1):
+            pre()
+            ctx.timer_start(); fn(); t = ctx.timer_stop()
+            if i:
+                best = t if best is None else min(best, t)
+        return best
+
+    def lu_case(n, dtype, **opt):
+        a = np.empty((n, n), dtype=dtype, order="F")
+        fill_random(a)
+        if opt.get("no_pivot"):
+            a[np.arange(n), np.arange(n)] += n / 4       # diagonally dominant: safe without pivoting
+        src = rfb200.DeviceMatrix(ctx, n, n, dtype, lda=n); src.upload(a); ctx.sync()
+        dst = rfb200.DeviceMatrix(ctx, n, n, dtype, lda=n)
+        ms = timed(lambda: dst.lu(**opt), lambda: dst.copy_from(src))
+        f, ipiv, info = dst.download()
+        res = hutchinson_residual(a.astype(np.float64), f.astype(np.float64),
+                                  np.arange(1, n + 1) if opt.get("no_pivot") else ipiv, nvec=4)
+        src.free(); dst.free()
+        return {"ms": round(ms, 3), "gflops": round(lu_flops(n) / ms / 1e6, 1), "info": info, "residual_fro_rel_est": res,
+                "bound_20_n_eps": 20 * n * float(np.finfo(dtype).eps)}
+
+    out["4096x4096 Float64 LU with partial pivoting (BASELINE config 2)"] = lu_case(4096, np.float64)
+    out["8192x8192 Float32 LU, exact FP32 FFMA trailing update (BASELINE config 5, default mode)"] = lu_case(8192, np.float32)
+    out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5, opt-in mode)"] = \
+        lu_case(8192, np.float32, f32_mode=1)
+    out["16384x16384 Float64 LU, pivot = Val(false) (src/lu.jl:27-65)"] = lu_case(16384, np.float64, no_pivot=1)
+    # butterfly transform: algorithmic bytes 2 * 8 * n^2
+    n = 16384
+    d = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
+    ctx.memset(d.ptr, 0, d.nbytes)
+    uv = rfb200.butterfly_generate_random(n)
+    duv = ctx.malloc(uv.nbytes); ctx.h2d(duv, uv); ctx.sync()
+    ms = timed(lambda: ctx._check(ctx._lib.rfb_butterfly_mul_f64(ctx.handle, C.c_void_p(d.ptr), n, n, C.c_void_p(duv))), lambda: None, reps=5)
+    out["16384x16384 Float64 butterfly transform U'AV (src/butterflylu.jl:93-113)"] = {
+        "ms": round(ms, 4), "GBps": round(16.0 * n * n / ms / 1e6, 1), "algorithmic_bytes": 16 * n * n}
+    ctx.free(duv); d.free()
+    # batched small LU: 16384 matrices of 32 x 32 Float64, one launch
+    batch, m = 16384, 32
+    a = np.random.default_rng(12).random((batch, m, m))
+    d0, d1 = ctx.malloc(a.nbytes), ctx.malloc(a.nbytes)
+    ctx.h2d(d0, a); ctx.sync()
+    piv, info = ctx.malloc(batch * m * 8), ctx.malloc(batch * 8)
+    opts = rfb200._make_opts(rfb200._lib.RFB_MEM_DEVICE)
+    ms = timed(lambda: ctx._check(ctx._lib.rfb_lu_batched_f64(ctx.handle, C.c_void_p(d1), m, m, m, m * m, batch, C.c_void_p(piv),
+                                                              C.c_void_p(info), C.byref(opts))),
+               lambda: ctx.d2d(d1, d0, a.nbytes))
+    out["16384 x (32x32 Float64) batched LU with partial pivoting, one launch"] = {
+        "ms": round(ms, 4), "matrices_per_s": round(batch / ms * 1e3), "gflops": round(batch * (2.0 * m ** 3 / 3) / ms / 1e6, 1)}
+    for p in (d0, d1, piv, info):
+        ctx.free(p)
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import rfb200
 
@@ -290,6 +353,11 @@ def run_ours(args, rank, world, local_rank):
                "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + n * 8 + 8,
                "pcie_h2d_GBps": n * n * 8 / h2d_s / 1e9, "pcie_d2h_GBps": n * n * 8 / d2h_s / 1e9}
 
+    # ---- the other single-GPU BASELINE configs and the widened rows, device resident (not the headline) ----
+    others = None
+    if world == 1 and not args.skip_others:
+        others = other_configs(ctx, rfb200)
+
     # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
     cpu = None
     if rank == 0 and not args.skip_cpu_baseline:
@@ -311,7 +379,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"input {n * n * 8 / 1e6:.0f} MB > 126 MB L2; matrix restored by an untimed d2d copy between steps",
                        "device": dev},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "checks": checks, "dmma_peak_tflops": dmma_peak,
+            "checks": checks, "dmma_peak_tflops": dmma_peak, "other_configs": others,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -482,6 +550,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-others", action="store_true", help="skip the informational other_configs block")
     ap.add_argument("--check-pivots", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
