@@ -257,78 +257,6 @@ trsm_upper_block_kernel(const T *__restrict__ U, int kb, T *__restrict__ B, long
     }
 }
 
-// Triangular block solve for a HANDFUL of right-hand sides (the vector / few-column `ldiv!(F, b)` of
-// src/lu.jl:60-64 and runtests.jl:21-28, :82, :122-127).  The column-parallel kernels above would run one
-// CTA with one active lane; here the parallelism is over ROWS: thread r owns row r of all (<= 8) right-hand
-// sides, column c of the triangle is one coalesced load (prefetched 16 columns ahead into registers, double
-// buffered), x_c is broadcast through shared memory, one barrier per column.  UPPER = false: unit lower
-// triangle, forward; UPPER = true: non-unit upper triangle, backward (x_c is divided by the diagonal first).
-constexpr int kVecRhs = 8;
-constexpr int kVecPF = 16;
-template <typename T, bool UPPER>
-__global__ void __launch_bounds__(256)
-trsv_block_kernel(const T *__restrict__ M, int kb, T *__restrict__ B, int nrhs, long long lda) {
-    __shared__ T sx[2][kVecRhs];
-    const int r = threadIdx.x;
-    const bool live = r < kb;
-    T x[kVecRhs];
-#pragma unroll
-    for (int q = 0; q < kVecRhs; ++q) x[q] = (live && q < nrhs) ? B[r + (long long)q * lda] : T(0);
-    // column visited at step t: forward c = t, backward c = kb - 1 - t
-    auto colof = [&](int t) { return UPPER ? kb - 1 - t : t; };
-    auto needs = [&](int c) { return live && (UPPER ? r <= c : r > c); };   // (UPPER: r == c reads the diagonal)
-    T buf[2][kVecPF];
-    auto prefetch = [&](int t0, T *dst) {
-#pragma unroll
-        for (int i = 0; i < kVecPF; ++i) {
-            const int t = t0 + i;
-            const int c = colof(t < kb ? t : kb - 1);
-            dst[i] = (t < kb && needs(c)) ? M[r + (long long)c * lda] : T(0);
-        }
-    };
-    prefetch(0, buf[0]);
-    for (int t0 = 0; t0 < kb; t0 += 2 * kVecPF) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int tb = t0 + half * kVecPF;
-            if (tb >= kb) break;
-            prefetch(tb + kVecPF, buf[half ^ 1]);                  // next 16 columns fly during these 16 steps
-#pragma unroll
-            for (int i = 0; i < kVecPF; ++i) {
-                const int t = tb + i;
-                if (t >= kb) break;
-                const int c = colof(t);
-                const T mv = buf[half][i];
-                if (r == c) {
-#pragma unroll
-                    for (int q = 0; q < kVecRhs; ++q) {
-                        if (UPPER) x[q] = x[q] / mv;               // back substitution divides by the diagonal
-                        sx[t & 1][q] = x[q];
-                    }
-                }
-                __syncthreads();
-                if (needs(c) && r != c) {
-#pragma unroll
-                    for (int q = 0; q < kVecRhs; ++q) x[q] = fma(-mv, sx[t & 1][q], x[q]);
-                }
-            }
-        }
-    }
-    if (live) {
-#pragma unroll
-        for (int q = 0; q < kVecRhs; ++q)
-            if (q < nrhs) B[r + (long long)q * lda] = x[q];
-    }
-}
-
-template <typename T, bool UPPER>
-int launch_trsv_block(rfb_ctx *ctx, const T *M, int kb, T *B, int64_t nrhs, int64_t lda) {
-    RfbLaunchScope scope(ctx, RFB_KC_TRSM, (double)kb * (double)kb * (double)nrhs);
-    trsv_block_kernel<T, UPPER><<<1, 256, 0, ctx->stream>>>(M, kb, B, (int)nrhs, lda);
-    RFB_CUDA(ctx, cudaGetLastError());
-    return RFB_OK;
-}
-
 template <typename T>
 int launch_upper_block(rfb_ctx *ctx, const T *U, int kb, T *B, int64_t nrhs, int64_t lda) {
     constexpr size_t smem = sizeof(T) * (kSub * kSub + 4 * kSub * kBlkCols);
@@ -342,10 +270,7 @@ int launch_upper_block(rfb_ctx *ctx, const T *U, int kb, T *B, int64_t nrhs, int
 
 template <typename T>
 int trsm_upper_rec(rfb_ctx *ctx, const T *U, int64_t k, T *B, int64_t nrhs, int64_t lda, const rfb_opts *opts) {
-    if (k <= 256) {
-        if (nrhs <= kVecRhs) return launch_trsv_block<T, true>(ctx, U, (int)k, B, nrhs, lda);
-        return launch_upper_block<T>(ctx, U, (int)k, B, nrhs, lda);
-    }
+    if (k <= 256) return launch_upper_block<T>(ctx, U, (int)k, B, nrhs, lda);
     int64_t k1 = ((k / 2 + 255) / 256) * 256;
     if (k1 >= k) k1 = ((k - 1) / 256) * 256;
     RFB_TRY(trsm_upper_rec<T>(ctx, U + k1 + k1 * lda, k - k1, B + k1, nrhs, lda, opts));        // bottom block first
@@ -371,7 +296,6 @@ int trsm_rec(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t ld
     if (k <= tb) {
         if (tb == 32) return launch_diag<T, 32>(ctx, L, (int)k, B, nrhs, lda);
         if (tb == 64) return launch_diag<T, 64>(ctx, L, (int)k, B, nrhs, lda);
-        if (nrhs <= kVecRhs && tb == 256) return launch_trsv_block<T, false>(ctx, L, (int)k, B, nrhs, lda);
         return launch_block<T>(ctx, L, (int)k, B, nrhs, lda);
     }
     // split at a multiple of the diagonal block nearest to k/2
