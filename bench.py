@@ -395,6 +395,8 @@ def run_ours_dist(args, rank, world, local_rank):
     import rfb200
     from rfb200.dist_lu import DistributedLU, block_range
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout; stdout carries ONE JSON line
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.n if args.n else 32768

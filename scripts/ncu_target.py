@@ -52,3 +52,12 @@ elif what == "batched":
     batch, m = int(sys.argv[2]), int(sys.argv[3])
     a = np.random.default_rng(1).random((batch, m, m))
     F = rfb200.lu_batched(a, ctx=ctx)
+elif what == "panel":
+    m, n = int(sys.argv[2]), int(sys.argv[3])
+    a = np.asfortranarray(np.random.default_rng(12).random((m, n)))
+    d = ctx.malloc(a.nbytes); ctx.h2d(d, a)
+    piv = ctx.malloc(n * 8); info = ctx.malloc(64); ctx.memset(info, 0, 64)
+    for _ in range(2):
+        ctx.h2d(d, a)
+        ctx._check(ctx._lib.rfb_panel_getrf_f64(ctx.handle, C.c_void_p(d), m, n, m, C.c_void_p(piv), 0, C.c_void_p(info), 0))
+    ctx.sync()
