@@ -1,0 +1,16 @@
+#!/bin/bash
+# run 22: two header polls in flight (staggered half a round trip)
+set -u
+cd /root/repo
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_lu.py -q -m gpu -x 2>&1 | tail -3
+PANEL_ONLY=1 timeout 300 python scripts/bench_kernels.py 2>&1 | tail -1
+for n in 4096 16384; do
+timeout 600 python bench.py --n $n --steps 5 --warmup 3 --skip-cpu-baseline --skip-others --skip-e2e > gpurun_out/bench_${n}_run22.json 2> gpurun_out/bench_${n}_run22.err; echo "bench rc=$?"
+done
+python - <<'PY'
+import json
+for f in ('gpurun_out/bench_4096_run22.json','gpurun_out/bench_16384_run22.json'):
+    d=json.load(open(f))
+    print({k:d[k] for k in ('value','ms_per_step')}, d['roofline']['share_of_step_ms'], d['checks'])
+PY
