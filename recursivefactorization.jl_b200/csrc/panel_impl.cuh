@@ -193,6 +193,14 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
     if (tid < NB) { sh.u[0][tid] = T(0); sh.u[1][tid] = T(0); }
     __syncthreads();
 
+    // Deferred window update: after pivot row k arrives a thread only computes its multiplier and its NEXT
+    // column value (cur0, one FMA) -- that is all the next pivot search needs -- and goes straight into the next
+    // reduction; the other up-to-62 FMAs of the rank-1 update (same formula, so reg[0] reproduces cur0 bit for bit)
+    // run after the next header is on its way, in the shadow of the header round trip instead of in front of it.
+    T cur0 = reg[0];
+    T pend_nl = T(0);
+    bool pending = false;
+
 #pragma unroll 1
     for (int k = 0; k < npiv; ++k) {
         const int par = k & 1;
@@ -200,17 +208,41 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         const unsigned int epoch = epoch_base + (unsigned int)k;
 
         // -- local candidate (src/lu.jl:296-305) ------------------------------------------------
-        const T av = fabs(reg[0]);
+        const T av = fabs(cur0);
         // Every candidate computes the reciprocal of ITS OWN value now: the ~7 dependent FP64 operations of
         // the correctly rounded reciprocal run in the shadow of the reduction / exchange below instead of
         // on the critical path after it (the winner's value is the one that gets used, :317-320).
-        const T myrinv = (reg[0] != T(0)) ? rcp_rn(reg[0]) : T(1);
+        const T myrinv = (cur0 != T(0)) ? rcp_rn(cur0) : T(1);
         Cand c;
         c.key = (alive && av > T(0)) ? to_bits(av) : 0ull;
         c.lp = alive ? logpos : kNone;
         c.src = (unsigned int)bid;
         const Cand cb = block_best<WARPS>(c, sh.loc[par], warp, lane);
         const bool cta_winner = alive && logpos == cb.lp;
+
+        // -- L2 exchange: this CTA's header goes out before anything else -----------------------------
+        if (!CLUSTER && G > 1) {
+            if (cta_winner) {
+                st_tagged(&x->header[par][bid].h[0], epoch, (unsigned int)cb.key, (unsigned int)(cb.key >> 32));
+                st_tagged(&x->header[par][bid].h[1], epoch, cb.lp, 0u);
+            } else if (cb.lp == kNone && tid == 0) {
+                st_tagged(&x->header[par][bid].h[0], epoch, 0u, 0u);
+                st_tagged(&x->header[par][bid].h[1], epoch, kNone, 0u);
+            }
+        }
+        // -- deferred rank-1 update of step k-1: slide the window, in chunks of 8 columns; a chunk runs iff it still
+        //    held live columns at step k-1 (warp-uniform; the publisher wrote exactly the same chunks, zeros beyond)
+        if (pending) {
+            const int remp = rem + 1;
+#pragma unroll
+            for (int c8 = 0; c8 < NB; c8 += 8)
+                if (c8 <= remp) {
+#pragma unroll
+                    for (int j = (c8 == 0 ? 1 : c8); j < c8 + 8; ++j) reg[j - 1] = fma(pend_nl, sh.u[par ^ 1][j], reg[j]);
+                }
+            reg[NB - 1] = T(0);
+            pending = false;
+        }
 
         Cand wb;
         if (CLUSTER) {
@@ -261,8 +293,6 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
         } else {
             // -- publish this CTA's candidate (header first, then its row window) ---------------
             if (cta_winner) {
-                st_tagged(&x->header[par][bid].h[0], epoch, (unsigned int)cb.key, (unsigned int)(cb.key >> 32));
-                st_tagged(&x->header[par][bid].h[1], epoch, cb.lp, 0u);
 #pragma unroll
                 for (int c8 = 0; c8 < NB; c8 += 8)
                     if (c8 < rem) {
@@ -270,9 +300,6 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
                         for (int j = c8; j < c8 + 8; ++j) sh.pub[j] = reg[j];
                     }
                 sh.pub[NB] = myrinv;
-            } else if (cb.lp == kNone && tid == 0) {
-                st_tagged(&x->header[par][bid].h[0], epoch, 0u, 0u);
-                st_tagged(&x->header[par][bid].h[1], epoch, kNone, 0u);
             }
             if (__ballot_sync(0xffffffffu, cta_winner)) {       // the winner's warp stores the row together
                 __syncwarp();
@@ -363,16 +390,21 @@ panel_kernel(T *__restrict__ A, int m, int n, long long lda, long long *__restri
             T l = reg[0];
             if (pv != T(0)) l *= sh.rinv[par];               // reciprocal scaling (:317-320)
             fin[k * THREADS + tid] = l;
-            const T nl = -l;
-            // slide the window, in chunks of 8 columns; a chunk runs iff it still holds live columns (8c <= rem:
-            // warp-uniform, and the publisher wrote exactly the same chunks, zeros beyond the live width)
+            pend_nl = -l;
+            if (G == 1 && !CLUSTER) {
+                // no exchange latency to hide behind: update the whole window now (one CTA / batched kernel)
 #pragma unroll
-            for (int c8 = 0; c8 < NB; c8 += 8)
-                if (c8 <= rem) {
+                for (int c8 = 0; c8 < NB; c8 += 8)
+                    if (c8 <= rem) {
 #pragma unroll
-                    for (int j = (c8 == 0 ? 1 : c8); j < c8 + 8; ++j) reg[j - 1] = fma(nl, sh.u[par][j], reg[j]);
-                }
-            reg[NB - 1] = T(0);
+                        for (int j = (c8 == 0 ? 1 : c8); j < c8 + 8; ++j) reg[j - 1] = fma(pend_nl, sh.u[par][j], reg[j]);
+                    }
+                reg[NB - 1] = T(0);
+                cur0 = reg[0];
+            } else {
+                cur0 = fma(pend_nl, sh.u[par][1], reg[1]);   // column k+1 after step k (:330-334); the rest is deferred
+                pending = true;
+            }
         }
         if (bid == 0 && tid == 0) {
             ipiv[k] = (long long)wb.lp + 1 + ipiv_add;
