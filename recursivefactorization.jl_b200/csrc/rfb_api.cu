@@ -35,16 +35,15 @@ struct LuPlan {
     int64_t n_total = 0;               // columns of the whole matrix
     // pipelined upload (host mode): column chunk i is resident once up_events[i] has fired
     std::vector<cudaEvent_t> *up_events = nullptr;
-    int64_t up_chunk = 0;  // columns per chunk
+    const std::vector<int64_t> *up_bounds = nullptr;   // up_bounds[i] = first column NOT covered by chunks 0..i
     int up_waited = -1;    // last chunk the compute stream already waits for
 };
 
 // The compute stream is about to touch columns [0, ncols): make it wait for their upload.
 static int need_cols(rfb_ctx *ctx, LuPlan &plan, int64_t ncols) {
     if (!plan.up_events || ncols <= 0) return RFB_OK;
-    int last = (int)((ncols - 1) / plan.up_chunk);
-    if (last >= (int)plan.up_events->size()) last = (int)plan.up_events->size() - 1;
-    while (plan.up_waited < last) {
+    const int nchunks = (int)plan.up_events->size();
+    while (plan.up_waited + 1 < nchunks && (plan.up_waited < 0 || (*plan.up_bounds)[plan.up_waited] < ncols)) {
         plan.up_waited++;
         RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, (*plan.up_events)[plan.up_waited], 0));
     }
@@ -72,7 +71,7 @@ int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv,
 //   right spine, rows [c0, c0 + n1) of every column are final and start travelling back to the host while
 //   the trailing update runs, instead of waiting for the end of the factorization.
 constexpr int64_t kEagerUnit = 512;
-constexpr int64_t kEarlyRowsMin = 1024;
+constexpr int64_t kEarlyRowsMin = 256;
 
 template <typename T>
 int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
@@ -113,12 +112,12 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
 
 template <typename T>
 int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d_ipiv, int64_t *d_info,
-              const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, int64_t up_chunk = 0,
+              const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, const std::vector<int64_t> *up_bounds = nullptr,
               T *host_A = nullptr, int64_t host_lda = 0, int64_t *early_rows = nullptr) {
     LuPlan plan;
     plan.opts = opts;
     plan.up_events = up_events;
-    plan.up_chunk = up_chunk;
+    plan.up_bounds = up_bounds;
     plan.host_A = host_A;
     plan.host_lda = host_lda;
     plan.host_m = m;
@@ -485,8 +484,20 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     // Pipelined upload: column chunks go up on the copy stream in order; the factorization is
     // left-looking, so it starts as soon as the first chunk is resident and the rest of the upload
     // hides behind the work on the left columns.
-    const int64_t chunk_cols = std::max<int64_t>(64, (int64_t)((size_t(64) << 20) / (sizeof(T) * (size_t)ldd)));
-    const int nchunks = (int)((n + chunk_cols - 1) / chunk_cols);
+    // Chunks grow geometrically from 8 MB to 64 MB: the first panel only waits for the first 8 MB.
+    std::vector<int64_t> bounds;
+    {
+        const size_t col_bytes = sizeof(T) * (size_t)ldd;
+        size_t target = size_t(8) << 20;
+        int64_t j = 0;
+        while (j < n) {
+            const int64_t nc = std::max<int64_t>(64, (int64_t)(target / col_bytes));
+            j = std::min<int64_t>(n, j + nc);
+            bounds.push_back(j);
+            if (target < (size_t(64) << 20)) target *= 2;
+        }
+    }
+    const int nchunks = (int)bounds.size();
     while ((int)ctx->up_events.size() < nchunks) {
         cudaEvent_t e;
         RFB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -495,7 +506,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));          // the staging buffer is free again
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
     for (int c = 0; c < nchunks; ++c) {
-        const int64_t j0 = (int64_t)c * chunk_cols, nc = std::min<int64_t>(chunk_cols, n - j0);
+        const int64_t j0 = c ? bounds[c - 1] : 0, nc = bounds[c] - j0;
         RFB_CUDA(ctx, cudaMemcpy2DAsync(dA + j0 * ldd, sizeof(T) * ldd, A + j0 * lda, sizeof(T) * lda, sizeof(T) * m,
                                         nc, cudaMemcpyHostToDevice, ctx->copy_stream));
         RFB_CUDA(ctx, cudaEventRecord(ctx->up_events[c], ctx->copy_stream));
@@ -506,7 +517,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     cudaPointerAttributes pattr;
     const bool pinned = cudaPointerGetAttributes(&pattr, A) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, nopiv ? nullptr : ctx->d_ipiv, ctx->d_info, opts, &evs, chunk_cols,
+    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, nopiv ? nullptr : ctx->d_ipiv, ctx->d_info, opts, &evs, &bounds,
                          (pinned && m >= n) ? A : nullptr, lda, &early_rows));
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
     // download what the early copies (rows [0, early_rows) of all columns) did not cover
