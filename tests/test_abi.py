@@ -34,6 +34,29 @@ def test_ctypes_table_matches_header():
     assert rfb200._lib.load().rfb_version() >= 100
 
 
+def test_option_struct_is_mirrored_field_for_field():
+    """`struct rfb_opts` in the header, the ctypes Structure and the Julia shim's RfbOpts must list the same fields in
+    the same order (a silent mismatch would shift every option by four bytes)."""
+    body = re.search(r"typedef struct rfb_opts \{(.*?)\} rfb_opts;", HEADER, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = re.findall(r"int32_t\s+([a-z_0-9]+)(?:\[(\d+)\])?;", body)
+    py_fields = [(n, str(t._length_) if hasattr(t, "_length_") else "") for n, t in rfb200.rfb_opts._fields_]
+    assert [(n, l) for n, l in c_fields] == py_fields
+    assert 4 * sum(int(l or 1) for _, l in c_fields) == 64
+    jl = open(os.path.join(ROOT, "recursivefactorization.jl_b200", "julia", "RecursiveFactorizationB200.jl")).read()
+    jbody = re.search(r"struct RfbOpts\n(.*?)\nend", jl, flags=re.S).group(1)
+    j_fields = re.findall(r"^\s*([a-z_0-9]+)::(Int32|NTuple\{(\d+), Int32\})", jbody, flags=re.M)
+    assert [(n, l) for n, _, l in j_fields] == [(n, l) for n, l in c_fields]
+
+
+def test_julia_shim_only_calls_exported_symbols():
+    jl = open(os.path.join(ROOT, "recursivefactorization.jl_b200", "julia", "RecursiveFactorizationB200.jl")).read()
+    called = set(re.findall(r"\(:(rfb_[a-z0-9_]+), librfb200\)", jl)) | set(re.findall(r"\(Float\d+, :(rfb_[a-z0-9_]+)\)", jl))
+    assert {"rfb_create", "rfb_lu_f64", "rfb_lu_f32", "rfb_solve_f64", "rfb_butterfly_solve_f64", "rfb_lu_batched_f64",
+            "rfb_panel_getrf_f64", "rfb_laswp_f64", "rfb_trsm_llnu_f64", "rfb_gemm_nn_sub_f64"} <= called
+    assert called <= set(declared_functions()), called - set(declared_functions())
+
+
 def test_no_oracle_or_cpu_fallback_in_product():
     pkg = os.path.join(ROOT, "recursivefactorization.jl_b200")
     for dirpath, _, files in os.walk(pkg):
