@@ -570,8 +570,10 @@ def lu_batched_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, *,
     batch, m, n = A.shape
     it = A.itemsize
     if batch and m and n:
-        if A.strides[1] != it or A.strides[2] < m * it or A.strides[2] % it or A.strides[0] % it or \
-                (batch > 1 and A.strides[0] < A.strides[2] * n) or not A.flags.writeable:
+        # (numpy reports arbitrary strides for length-1 axes: only constrain the axes that are actually walked)
+        bad = (m > 1 and A.strides[1] != it) or (n > 1 and (A.strides[2] < m * it or A.strides[2] % it)) or \
+            (batch > 1 and (A.strides[0] % it or A.strides[0] < (A.strides[2] if n > 1 else m * it) * n)) or not A.flags.writeable
+        if bad:
             raise TypeError("each A[b] must be a writeable column-major matrix (strides (s, itemsize, lda*itemsize))")
     mn = min(m, n)
     if piv:
@@ -583,8 +585,8 @@ def lu_batched_(A: np.ndarray, ipiv: Optional[np.ndarray] = None, pivot=True, *,
     ctx = ctx or default_context()
     lib = ctx._lib
     fn = lib.rfb_lu_batched_f64 if A.dtype == np.float64 else lib.rfb_lu_batched_f32
-    lda = A.strides[2] // it if (m and n) else max(m, 1)
-    stride = A.strides[0] // it if (batch and m and n) else lda * max(n, 1)
+    lda = A.strides[2] // it if (m and n > 1) else max(m, 1)
+    stride = A.strides[0] // it if (batch > 1 and m and n) else lda * max(n, 1)
     opts = _make_opts(_lib.RFB_MEM_HOST, no_pivot=not piv)
     ctx._check(fn(ctx.handle, C.c_void_p(A.ctypes.data) if A.size else None, m, n, lda, stride, batch,
                   C.c_void_p(ipiv.ctypes.data) if (piv and ipiv.size) else None, C.c_void_p(info.ctypes.data), C.byref(opts)))
