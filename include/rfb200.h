@@ -197,6 +197,19 @@ int rfb_copy2d(rfb_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, 
 /* enqueue on a caller-provided CUDA stream (e.g. torch's current stream); NULL restores the own one */
 int rfb_set_stream(rfb_ctx *ctx, void *cuda_stream);
 
+/* ---- host-driver trace (no GPU needed) -------------------------------------------------------------------
+ * Runs the host recursion of rfb_lu_* (twin of src/lu.jl:97-156 and :189-263) for an m x n matrix WITHOUT launching
+ * anything and returns the sequence of operations it would enqueue, 8 int64 per operation:
+ *   [0] op: 1 panel getrf (src/lu.jl:290-338), 2 unpivoted panel, 3 row interchanges (:164-188), 4 unit-lower TRSM
+ *       (:235, :153), 5 Schur update (:265-284), 6 early download of finished rows (host mode), 7 identity ipiv fill
+ *   [1],[2] row, column of the first operand (panel / swapped block / L / C); [6],[7] of the second (B of the TRSM,
+ *       A of the update, whose B is at row [7], column [2]);  [3],[4],[5] sizes: panel m, n, column offset; laswp
+ *       ncols, first pivot, one past the last pivot; TRSM k, nrhs; update m, n, k; download first row ([1]), rows, cols.
+ * `pinned_host` selects the schedule used for page-locked host matrices (eager interchanges + early row downloads).
+ * Used by the CPU tests to replay the schedule with the oracle's kernels and compare with the oracle's own LU. */
+int rfb_trace_lu(int is_f32, int64_t m, int64_t n, int64_t lda, const rfb_opts *opts, int pinned_host, int64_t *ops,
+                 int64_t cap, int64_t *count);
+
 /* ---- memory / stream plumbing ------------------------------------------------------------- */
 int rfb_malloc(rfb_ctx *ctx, void **dev_ptr, size_t bytes);
 int rfb_free(rfb_ctx *ctx, void *dev_ptr);

@@ -38,7 +38,7 @@ __all__ = [
     "lu", "lu_", "ldiv_", "LU", "SingularException", "ZeroPivotException", "RfbError", "Context", "default_context",
     "DeviceMatrix", "nsplit", "RowMaximum", "NoPivot", "NotIPIV", "Adjoint", "Transpose", "AdjointLU",
     "ButterflyWorkspace", "butterfly_workspace", "butterfly_solve_", "butterfly_mul_", "butterfly_generate_random",
-    "lu_batched_", "lu_batched",
+    "lu_batched_", "lu_batched", "trace_lu",
 ]
 
 
@@ -469,6 +469,26 @@ def lu(A, pivot=True, thread=False, **kwargs):
     if A.ndim != 2:
         raise TypeError("A must be a matrix")
     return lu_(np.array(A, order="F", copy=True), None, pivot, thread, **kwargs)
+
+
+def trace_lu(m: int, n: int, dtype=np.float64, pinned_host: bool = False, lda: Optional[int] = None, **opt_kw) -> np.ndarray:
+    """The launch sequence `rfb_lu_*` would enqueue for an m x n matrix, without a GPU (`rfb_trace_lu`): an (nops, 8)
+    int64 array, see include/rfb200.h.  `pinned_host=True` gives the schedule used for page-locked host matrices."""
+    lib = _lib.load()
+    lda = lda if lda is not None else max(m, 1)
+    opts = _make_opts(_lib.RFB_MEM_DEVICE, **opt_kw)
+    count = C.c_int64(0)
+    is_f32 = int(np.dtype(dtype) == np.float32)
+    rc = lib.rfb_trace_lu(is_f32, m, n, lda, C.byref(opts), int(pinned_host), None, 0, C.byref(count))
+    if rc != _lib.RFB_OK:
+        raise RfbError(rc, "rfb_trace_lu failed")
+    ops = np.zeros((count.value, 8), dtype=np.int64)
+    if count.value:
+        rc = lib.rfb_trace_lu(is_f32, m, n, lda, C.byref(opts), int(pinned_host), C.c_void_p(ops.ctypes.data), count.value,
+                              C.byref(count))
+        if rc != _lib.RFB_OK:
+            raise RfbError(rc, "rfb_trace_lu failed")
+    return ops
 
 
 # ----------------------------------------------------------------------------------------------

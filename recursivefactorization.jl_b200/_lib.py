@@ -70,6 +70,7 @@ SIGNATURES = {
     "rfb_butterfly_solve_f32": (_int, [_p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_batched_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_batched_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
+    "rfb_trace_lu": (_int, [_int, _i64, _i64, _i64, C.POINTER(rfb_opts), _int, _p, _i64, C.POINTER(_i64)]),
     "rfb_lu_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_range_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_laswp_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),

@@ -262,6 +262,7 @@ template <>
 int rfb_launch_gemm<double>(rfb_ctx *ctx, double *C, const double *A, const double *B, int64_t m, int64_t n,
                             int64_t k, int64_t lda, const rfb_opts *opts) {
     if (m <= 0 || n <= 0 || k <= 0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_GEMM, C, A, B, m, n, k); return RFB_OK; }
     const int path = opts ? opts->gemm_path : 0;
     if (n <= RFB_SKINNY_MAX_N && path == 0) return rfb_launch_gemm_skinny<double>(ctx, C, A, B, m, n, k, lda);   // GEMV-shaped: HBM-bound
     if (path != 1) {
@@ -282,6 +283,7 @@ template <>
 int rfb_launch_gemm<float>(rfb_ctx *ctx, float *C, const float *A, const float *B, int64_t m, int64_t n,
                            int64_t k, int64_t lda, const rfb_opts *opts) {
     if (m <= 0 || n <= 0 || k <= 0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_GEMM, C, A, B, m, n, k); return RFB_OK; }
     if (n <= RFB_SKINNY_MAX_N && !(opts && opts->gemm_path != 0)) return rfb_launch_gemm_skinny<float>(ctx, C, A, B, m, n, k, lda);
     if (opts && opts->f32_mode == RFB_F32_TF32X3) {
         bool handled = false;

@@ -90,6 +90,7 @@ template <typename T>
 int rfb_launch_laswp(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
                      int64_t npiv, int64_t ipiv_sub) {
     if (ncols <= 0 || npiv <= 0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_LASWP, A, nullptr, nullptr, ncols, ipiv_sub, ipiv_sub + npiv); return RFB_OK; }
     const unsigned int blocks = (unsigned int)((ncols + kLaswpThreads - 1) / kLaswpThreads);
     RfbLaunchScope scope(ctx, RFB_KC_LASWP, 4.0 * sizeof(T) * (double)npiv * (double)ncols);
     laswp_ipiv_kernel<T><<<blocks, kLaswpThreads, 0, ctx->stream>>>(A, ncols, lda, (const long long *)ipiv_dev,
@@ -101,6 +102,7 @@ int rfb_launch_laswp(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64
 template <typename T>
 int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1) {
     if (ncols <= 0 || k1 <= k0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_LASWP, A, nullptr, nullptr, ncols, k0, k1); return RFB_OK; }
     const unsigned int blocks = (unsigned int)((ncols + kListWarps - 1) / kListWarps);
     RfbLaunchScope scope(ctx, RFB_KC_LASWP, 4.0 * sizeof(T) * (double)(k1 - k0) * (double)ncols);
     laswp_list_kernel<T><<<blocks, kListWarps * 32, 0, ctx->stream>>>(A, ncols, lda, ctx->perm_dst, ctx->perm_src,

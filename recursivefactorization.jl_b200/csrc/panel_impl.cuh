@@ -582,6 +582,7 @@ template <typename T>
 int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipiv_dev,
                      int64_t ipiv_add, int64_t *info_dev, int64_t col_offset, int64_t perm_row0) {
     if (n <= 0 || m <= 0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_PANEL, A, nullptr, nullptr, m, n, col_offset); return RFB_OK; }
     PanelPermOut perm{nullptr, nullptr, nullptr, 0};
     if (perm_row0 >= 0 && ctx->perm_dst != nullptr) {     // whole-path driver: also emit the exchange list
         perm.dst = ctx->perm_dst + 2 * perm_row0;
@@ -630,6 +631,7 @@ int rfb_launch_panel(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
 
 template <typename T>
 int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m) {
+    if (ctx->dry_run) return m <= 148 * 256 ? 64 : (m <= 2 * 148 * 256 ? 32 : 16);   // nominal B200 capacities
     const int64_t g128 = (m + 127) / 128, g256 = (m + 255) / 256;
     if (g128 <= panel_capacity<T, 64, 128>(ctx) || g256 <= panel_capacity<T, 64, 256>(ctx)) return 64;
     if (g128 <= panel_capacity<T, 32, 128>(ctx) || g256 <= panel_capacity<T, 32, 256>(ctx)) return 32;

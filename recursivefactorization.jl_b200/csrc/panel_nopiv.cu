@@ -146,6 +146,7 @@ int rfb_launch_panel_nopiv(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda
     if (n <= 0 || m <= 0) return RFB_OK;
     if (n > RFB_MAX_NB) return ctx->fail(RFB_ERR_UNSUPPORTED, "panel width %lld > %d", (long long)n, RFB_MAX_NB);
     if (m < n) return ctx->fail(RFB_ERR_ARG, "panel needs m >= n (got %lld x %lld)", (long long)m, (long long)n);
+    if (ctx->dry_run) { ctx->rec(RFB_T_PANEL_NOPIV, A, nullptr, nullptr, m, n, col_offset); return RFB_OK; }
     if (n <= 16) return launch_inst<T, 16>(ctx, A, (int)m, (int)n, lda, info_dev, col_offset);
     if (n <= 32) return launch_inst<T, 32>(ctx, A, (int)m, (int)n, lda, info_dev, col_offset);
     return launch_inst<T, 64>(ctx, A, (int)m, (int)n, lda, info_dev, col_offset);
@@ -155,6 +156,7 @@ template int rfb_launch_panel_nopiv<float>(rfb_ctx *, float *, int64_t, int64_t,
 
 int rfb_launch_iota(rfb_ctx *ctx, int64_t *p_dev, int64_t n, int64_t first) {
     if (n <= 0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_IOTA, nullptr, nullptr, nullptr, n, first, 0); return RFB_OK; }
     RfbLaunchScope scope(ctx, RFB_KC_OTHER);
     iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((long long *)p_dev, n, first);
     RFB_CUDA(ctx, cudaGetLastError());

@@ -98,11 +98,18 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
     if (plan.host_A && eager_left == 0 && c0 == plan.early_rows && c0 + n == plan.n_total && n1 >= kEarlyRowsMin) {
         // right-spine node, pinned host matrix: rows [c0, c0 + n1) of ALL columns are final now (L and U11 on the
         // left, U12 on the right; everything still to come touches rows >= c0 + n1 only).
+        if (ctx->dry_run) {
+            RfbTraceOp o{};
+            o.v[0] = RFB_T_DOWNLOAD_ROWS; o.v[1] = c0; o.v[3] = n1; o.v[4] = plan.n_total;
+            ctx->trace.push_back(o);
+            plan.early_rows = c0 + n1;
+        } else {
         RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
         RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
         RFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<T *>(plan.host_A) + c0, sizeof(T) * plan.host_lda, root + c0,
                                         sizeof(T) * lda, sizeof(T) * n1, plan.n_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
         plan.early_rows = c0 + n1;
+        }
     }
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan, eager_left));   // :244
@@ -132,12 +139,12 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
             return ctx->fail(RFB_ERR_UNSUPPORTED, "%lld rows exceed the panel kernel's one-row-per-thread capacity", (long long)m);
         if (plan.leaf > fit) plan.leaf = fit;
     }
-    RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t), ctx->stream));
+    if (!ctx->dry_run) RFB_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int64_t), ctx->stream));
     const int64_t mn = m < n ? m : n;
     if (mn == 0) return RFB_OK;
     plan.lists = plan.pivot && !(opts && opts->laswp_path == 1);
     if (!plan.pivot && d_ipiv) RFB_TRY(rfb_launch_iota(ctx, d_ipiv, mn, 1));               // :107-113
-    if (plan.lists) {
+    if (plan.lists && !ctx->dry_run) {
         if ((size_t)mn > ctx->perm_cap) {
             if (ctx->perm_external) return ctx->fail(RFB_ERR_ARG, "caller-provided exchange-list buffers are too small");
             RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -640,6 +647,36 @@ int rfb_set_default_opts(rfb_ctx *ctx, const rfb_opts *opts) {
     if (!ctx) return RFB_ERR_ARG;
     if (opts) ctx->default_opts = *opts;
     else ctx->default_opts = rfb_opts{};
+    return RFB_OK;
+}
+
+int rfb_trace_lu(int is_f32, int64_t m, int64_t n, int64_t lda, const rfb_opts *opts, int pinned_host, int64_t *ops,
+                 int64_t cap, int64_t *count) {
+    if (!count || m < 0 || n < 0 || lda < (m > 1 ? m : 1)) return RFB_ERR_ARG;
+    rfb_ctx ctx;                                   // never touches CUDA: dry_run short-circuits every launcher
+    ctx.dry_run = true;
+    ctx.trace_lda = lda;
+    ctx.trace_elt = is_f32 ? 4 : 8;
+    char *base = reinterpret_cast<char *>(uintptr_t(1) << 40);       // fake address, never dereferenced
+    ctx.trace_base = base;
+    int64_t *fake_piv = reinterpret_cast<int64_t *>(uintptr_t(1) << 39);
+    int rc;
+    if (is_f32) {
+        float *A = reinterpret_cast<float *>(base);
+        rc = lu_device<float>(&ctx, A, m, n, lda, (opts && opts->no_pivot) ? nullptr : fake_piv, fake_piv, opts, nullptr, nullptr,
+                              pinned_host ? A : nullptr, lda, nullptr);
+    } else {
+        double *A = reinterpret_cast<double *>(base);
+        rc = lu_device<double>(&ctx, A, m, n, lda, (opts && opts->no_pivot) ? nullptr : fake_piv, fake_piv, opts, nullptr, nullptr,
+                               pinned_host ? A : nullptr, lda, nullptr);
+    }
+    if (rc != RFB_OK) return rc;
+    *count = (int64_t)ctx.trace.size();
+    if (ops) {
+        const int64_t nout = *count < cap ? *count : cap;
+        for (int64_t i = 0; i < nout; ++i)
+            for (int j = 0; j < 8; ++j) ops[8 * i + j] = ctx.trace[(size_t)i].v[j];
+    }
     return RFB_OK;
 }
 

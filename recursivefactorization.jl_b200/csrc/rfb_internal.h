@@ -34,6 +34,14 @@ struct RfbPanelXchg {
     unsigned int pad[3];                  // pad[0]: "diagonal block loaded" counter of the unpivoted panel kernel
 };
 
+// Dry-run trace of the host driver (rfb_trace_lu): the launchers record what they WOULD launch instead of
+// launching it, so the recursion of rfb_api.cu can be replayed and checked on a machine without a GPU.
+enum RfbTraceOpCode { RFB_T_PANEL = 1, RFB_T_PANEL_NOPIV = 2, RFB_T_LASWP = 3, RFB_T_TRSM_LOWER = 4, RFB_T_GEMM = 5,
+                      RFB_T_DOWNLOAD_ROWS = 6, RFB_T_IOTA = 7 };
+struct RfbTraceOp {
+    int64_t v[8];   // v[0] = op code; operands are (row, col) offsets into the traced matrix and sizes (see rfb200.h)
+};
+
 enum RfbKernelClass { RFB_KC_PANEL = 0, RFB_KC_LASWP = 1, RFB_KC_TRSM = 2, RFB_KC_GEMM = 3, RFB_KC_OTHER = 4, RFB_KC_COUNT = 8 };
 
 struct rfb_ctx {
@@ -84,6 +92,28 @@ struct rfb_ctx {
 
     // TMA
     void *encode_tiled = nullptr;         // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+
+    // dry run (rfb_trace_lu): no CUDA calls at all, launches are recorded
+    bool dry_run = false;
+    std::vector<RfbTraceOp> trace;
+    const char *trace_base = nullptr;     // fake base address of the traced matrix
+    int64_t trace_lda = 0;
+    size_t trace_elt = 8;
+    void rec(int op, const void *p0, const void *p1, const void *p2, int64_t a, int64_t b, int64_t c) {
+        auto rc = [&](const void *p, int64_t &r, int64_t &cc) {
+            if (!p) { r = cc = -1; return; }
+            const int64_t off = (int64_t)((reinterpret_cast<const char *>(p) - trace_base) / (int64_t)trace_elt);
+            r = off % trace_lda; cc = off / trace_lda;
+        };
+        RfbTraceOp o{};
+        o.v[0] = op;
+        int64_t r, cc;
+        rc(p0, r, cc); o.v[1] = r; o.v[2] = cc;
+        if (p1) { rc(p1, r, cc); o.v[6] = r; o.v[7] = cc; }
+        (void)p2;
+        o.v[3] = a; o.v[4] = b; o.v[5] = c;
+        trace.push_back(o);
+    }
 
     int fail(int code, const char *fmt, ...);
 };

@@ -312,6 +312,7 @@ template <typename T>
 int rfb_launch_trsm(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t lda,
                     const rfb_opts *opts) {
     if (k <= 0 || nrhs <= 0) return RFB_OK;
+    if (ctx->dry_run) { ctx->rec(RFB_T_TRSM_LOWER, L, B, nullptr, k, nrhs, 0); return RFB_OK; }
     int tb = 256;                                    // default: fused 256-row block solve
     if (opts && (opts->trsm_block == 32 || opts->trsm_block == 64 || opts->trsm_block == 128)) tb = opts->trsm_block;
     return trsm_rec<T>(ctx, L, k, B, nrhs, lda, tb, opts);
