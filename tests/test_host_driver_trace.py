@@ -114,3 +114,23 @@ def test_schedule_shape_facts():
     # Float32 splits at multiples of 16 (src/lu.jl:158-162)
     f32 = rfb200.trace_lu(8192, 8192, np.float32)
     assert (f32[f32[:, 0] == PANEL][:, 4] <= 64).all()
+
+
+@pytest.mark.parametrize("opt", [dict(leaf_width=16), dict(leaf_width=32), dict(laswp_path=1)])
+def test_driver_options_replay(opt):
+    """leaf_width (the GPU analogue of the reference's `blocksize`, src/lu.jl:101) and the ipiv-driven laswp path."""
+    m = n = 333
+    a0 = rand_matrix(np.random.default_rng([43, m]), m, n, np.float64)
+    ops = rfb200.trace_lu(m, n, np.float64, **opt)
+    leaf = opt.get("leaf_width", 64)
+    assert (ops[ops[:, 0] == PANEL][:, 4] <= leaf).all()
+    got, ipiv, info, _ = replay(a0.copy(order="F"), ops)
+    want, wp, winfo = O.lu_c(a0.copy(order="F"), blocksize=leaf, threshold=1)
+    assert info == winfo == 0 and np.array_equal(ipiv, wp) and np.array_equal(got, want)
+
+
+def test_very_tall_matrices_narrow_the_leaf_in_the_schedule():
+    """One row per thread of a cooperative grid: beyond 148 x 256 rows the driver narrows the leaf."""
+    assert (rfb200.trace_lu(30000, 128)[:, 4][rfb200.trace_lu(30000, 128)[:, 0] == PANEL] == 64).all()
+    ops = rfb200.trace_lu(50000, 128)
+    assert (ops[ops[:, 0] == PANEL][:, 4] <= 32).all()
