@@ -66,6 +66,26 @@ def hutchinson_residual(a0, factors, ipiv, nvec=8, seed=0):
     return float(np.linalg.norm(pax - lux) / np.sqrt(nvec) / np.linalg.norm(a0))
 
 
+def near_tie(a0, factors, ipiv, want_ipiv, k):
+    """Is the first differing pivot step k a near-tie?  The row the other implementation moved to position k must
+    have |L| >= 1 - 20 n eps in OUR factorization (the two candidates were equal to within the factorization's own
+    error); everything after a legitimate near-tie diverges by construction and is covered by the residual."""
+    m, n = a0.shape
+
+    def perm(ip, upto):
+        p = np.arange(m)
+        for i in range(upto):
+            j = int(ip[i]) - 1
+            if j != i:
+                p[i], p[j] = p[j], p[i]
+        return p
+    orig = perm(want_ipiv, k + 1)[k]
+    pos = int(np.nonzero(perm(ipiv, len(ipiv)) == orig)[0][0])
+    if pos <= k:
+        return False
+    return abs(float(factors[pos, k])) >= 1.0 - 20 * max(m, n) * float(np.finfo(a0.dtype).eps)
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -129,18 +149,57 @@ def cpu_baseline(n_sample, threads, reps=1):
     return lu_flops(n_sample) / best / 1e9, best
 
 
+def run_julia_reference(args):
+    """The real reference (baseline/run_reference.jl -> RecursiveFactorization.lu!) when a Julia runtime with an
+    instantiated environment exists under baseline/_ref.  Neither exists in the build image or on the GPU boxes
+    (SURVEY.md F2/F3), so this normally returns None and the C port is timed instead."""
+    import shutil
+    julia = shutil.which("julia")
+    proj = os.path.join(ROOT, "baseline", "_ref")
+    if not julia or not os.path.exists(os.path.join(proj, "Project.toml")):
+        return None
+    try:
+        res = subprocess.run([julia, f"--project={proj}", "-t", "auto", os.path.join(ROOT, "baseline", "run_reference.jl"),
+                              str(args.n), str(args.steps), str(args.warmup)], capture_output=True, text=True,
+                             timeout=max(600.0, 2 * args.ref_budget_s))
+        d = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception:
+        return None
+    cores = int(d.get("threads", os.cpu_count() or 1))
+    sample = (f"{args.n}x{args.n} Float64 U[0,1) LU per step (the whole workload), RecursiveFactorization.lu! "
+              f"{d.get('version', '')} (the unmodified Julia reference), {cores} Julia threads")
+    return {
+        "impl": "reference", "metric": METRIC, "value": d["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": d["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.n}x{args.n} Float64 LU with partial pivoting", "sample_n": args.n, "same_config": True},
+        "same_config": True,
+        "cpu_baseline": {"value": d["value"], "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
 def run_reference(args, rank, world):
+    """Reference arm: the CPU port of the reference algorithm on all host cores.  Same config as the product arm
+    (args.n) whenever steps + warmup factorizations at the calibrated rate fit the time budget; otherwise the largest
+    sample that does, and then the sample size is part of `config.workload` and `same_config` is false."""
     if rank != 0:
+        return
+    real = run_julia_reference(args)
+    if real is not None:
+        print(json.dumps(real))
         return
     from oracle import rf_oracle as O
     cores = os.cpu_count() or 1
-    # calibrate on a small case, then size the sample so the whole run stays within ~2.5 minutes
-    gf_small, _ = cpu_baseline(2048, cores)
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    cpu_baseline(2048, cores)                         # first call: thread pool start-up, page faults
+    gf_cal, _ = cpu_baseline(4096, cores)             # calibration (the port's rate still grows a little beyond this size)
+    budget_s = args.ref_budget_s / max(1, args.steps + args.warmup)
     n_s = 2048
-    for cand in (3072, 4096, 6144, 8192, 12288, 16384):
-        if cand <= args.n and lu_flops(cand) / (gf_small * 1e9) <= budget_s:
+    for cand in (3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768):
+        if cand <= args.n and lu_flops(cand) / (gf_cal * 1e9) <= budget_s:
             n_s = cand
+    if lu_flops(args.n) / (gf_cal * 1e9) <= budget_s:
+        n_s = args.n
     a0 = np.empty((n_s, n_s), dtype=np.float64, order="F")
     fill_random(a0)
     times = []
@@ -153,14 +212,20 @@ def run_reference(args, rank, world):
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = lu_flops(n_s) / (ms * 1e-3) / 1e9
-    sample = (f"{n_s}x{n_s} Float64 U[0,1) LU per step (bounded sample of the {args.n}x{args.n} workload), "
+    same = n_s == args.n
+    what = "the whole workload" if same else f"bounded sample of the {args.n}x{args.n} workload"
+    sample = (f"{n_s}x{n_s} Float64 U[0,1) LU per step ({what}), "
               f"oracle/rf_oracle.c = C restatement of src/lu.jl with reference defaults (blocksize 8, threshold 48), "
               f"OpenMP {cores} threads; the Julia reference itself cannot run here")
+    workload = f"{args.n}x{args.n} Float64 LU with partial pivoting"
+    if not same:
+        workload += f" -- CPU arm timed on a {n_s}x{n_s} SAMPLE of it (rate, not time, is comparable)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.n}x{args.n} Float64 LU with partial pivoting", "sample_n": n_s},
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "sample_n": n_s, "same_config": same},
+        "same_config": same,
         "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -183,7 +248,7 @@ def other_configs(ctx, rfb200):
                 best = t if best is None else min(best, t)
         return best
 
-    def lu_case(n, dtype, **opt):
+    def lu_case(n, dtype, check=None, **opt):
         a = np.empty((n, n), dtype=dtype, order="F")
         fill_random(a)
         if opt.get("no_pivot"):
@@ -195,13 +260,29 @@ def other_configs(ctx, rfb200):
         res = hutchinson_residual(a.astype(np.float64), f.astype(np.float64),
                                   np.arange(1, n + 1) if opt.get("no_pivot") else ipiv, nvec=4)
         src.free(); dst.free()
-        return {"ms": round(ms, 3), "gflops": round(lu_flops(n) / ms / 1e6, 1), "info": info, "residual_fro_rel_est": res,
-                "bound_20_n_eps": 20 * n * float(np.finfo(dtype).eps)}
+        out = {"ms": round(ms, 3), "gflops": round(lu_flops(n) / ms / 1e6, 1), "info": info, "residual_fro_rel_est": res,
+               "bound_20_n_eps": 20 * n * float(np.finfo(dtype).eps)}
+        if check and not opt.get("no_pivot"):
+            from scipy.linalg import lapack
+            getrf = lapack.dgetrf if dtype == np.float64 else lapack.sgetrf
+            _, piv, _ = getrf(a.copy(order="F"), overwrite_a=True)
+            out["pivots_equal_lapack"] = bool(np.array_equal(ipiv, piv + 1))
+            if not out["pivots_equal_lapack"]:
+                # Float32: rounding noise of different summation orders reaches the gap between the two largest
+                # candidates of a column; report where, and whether that step is a near-tie
+                k = int(np.argmax(ipiv != piv + 1))
+                out["first_pivot_mismatch"] = k
+                out["mismatch_is_near_tie"] = bool(near_tie(a, f, ipiv, piv + 1, k))
+            if check == "oracle":
+                from oracle import rf_oracle as O
+                _, want_p, _ = O.lu_c(a.copy(order="F"), threads=os.cpu_count() or 1)
+                out["pivots_equal_oracle"] = bool(np.array_equal(ipiv, want_p))
+        return out
 
-    out["4096x4096 Float64 LU with partial pivoting (BASELINE config 2)"] = lu_case(4096, np.float64)
-    out["8192x8192 Float32 LU, exact FP32 FFMA trailing update (BASELINE config 5, default mode)"] = lu_case(8192, np.float32)
+    out["4096x4096 Float64 LU with partial pivoting (BASELINE config 2)"] = lu_case(4096, np.float64, check="oracle")
+    out["8192x8192 Float32 LU, exact FP32 FFMA trailing update (BASELINE config 5, default mode)"] = lu_case(8192, np.float32, check="lapack")
     out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5, opt-in mode)"] = \
-        lu_case(8192, np.float32, f32_mode=1)
+        lu_case(8192, np.float32, check="lapack", f32_mode=1)
     out["16384x16384 Float64 LU, pivot = Val(false) (src/lu.jl:27-65)"] = lu_case(16384, np.float64, no_pivot=1)
     # butterfly transform: algorithmic bytes 2 * 8 * n^2
     n = 16384
@@ -294,10 +375,13 @@ def run_ours(args, rank, world, local_rank):
     lmax = float(np.abs(np.tril(f, -1)).max())
     checks = {"info": info, "residual_fro_rel_est": res, "bound_20_n_eps": 20 * n * float(np.finfo(np.float64).eps),
               "max_abs_L": lmax}
-    if args.check_pivots:
+    if args.check_pivots:                       # north_star: "pivot indices bit-exact" -- at the headline size, every run
         from scipy.linalg import lapack
         _, piv, _ = lapack.dgetrf(np.array(host, order="F", copy=True), overwrite_a=True)
         checks["pivots_equal_lapack"] = bool(np.array_equal(ipiv, piv + 1))
+        if not checks["pivots_equal_lapack"]:
+            checks["first_pivot_mismatch"] = int(np.argmax(ipiv != piv + 1))
+        del piv
     del f
 
     # ---- per-kernel-class profile (events around every launch; separate, untimed pass) ---------
@@ -553,7 +637,12 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-others", action="store_true", help="skip the informational other_configs block")
-    ap.add_argument("--check-pivots", action="store_true")
+    ap.add_argument("--check-pivots", dest="check_pivots", action="store_true", default=True,
+                    help="compare the pivot vector of the timed factorization with LAPACK dgetrf (default: on)")
+    ap.add_argument("--no-check-pivots", dest="check_pivots", action="store_false")
+    ap.add_argument("--ref-budget-s", type=float, default=900.0,
+                    help="reference arm: wall-clock budget for all its factorizations; the arm runs the same size as the "
+                         "product arm when that fits")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

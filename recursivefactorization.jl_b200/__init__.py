@@ -27,6 +27,7 @@ of the dot); ``import rfb200`` (repo-root shim) loads it.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -151,6 +152,13 @@ def nsplit(dtype, n: int) -> int:
 # ----------------------------------------------------------------------------------------------
 # context
 # ----------------------------------------------------------------------------------------------
+def _free_pinned(lib, addr: int):
+    try:
+        lib.rfb_host_free(None, C.c_void_p(addr))      # a NULL context is allowed: cudaFreeHost needs none
+    except Exception:
+        pass
+
+
 class Context:
     """Owns one ``rfb_ctx`` (stream + device workspaces) on one GPU.  Not thread-safe."""
 
@@ -165,7 +173,6 @@ class Context:
                 self._h = C.c_void_p()
             raise RfbError(rc, msg)
         self.device = device
-        self._pinned = []
 
     # -- plumbing -------------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -178,9 +185,6 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            for addr in getattr(self, "_pinned", []):
-                self._lib.rfb_host_free(self._h, C.c_void_p(addr))
-            self._pinned = []
             self._lib.rfb_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -215,15 +219,17 @@ class Context:
         self._check(self._lib.rfb_free(self._h, C.c_void_p(ptr)))
 
     def pinned_empty(self, shape, dtype, order="F") -> np.ndarray:
-        """numpy array over page-locked host memory (cudaHostAlloc); released when the context closes."""
+        """numpy array over page-locked host memory (cudaHostAlloc); released when the array is collected."""
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
         p = C.c_void_p()
         self._check(self._lib.rfb_host_alloc(self._h, C.byref(p), max(n, 16)))
         buf = (C.c_byte * max(n, 16)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape, order=order)
-        self._pinned.append(p.value)         # released in close()
-        return arr
+        # The allocation lives as long as any array (or view, or LU.factors) built over `buf`: numpy keeps `buf`
+        # alive through .base, and the finalizer frees the page-locked block when the last of them is collected --
+        # never while a view can still be dereferenced (closing the context does not free it).
+        weakref.finalize(buf, _free_pinned, self._lib, p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape, order=order)
 
     def h2d(self, dst: int, src: np.ndarray):
         self._check(self._lib.rfb_h2d(self._h, C.c_void_p(dst), C.c_void_p(src.ctypes.data), src.nbytes))
@@ -380,6 +386,23 @@ def _make_opts(mem_space=_lib.RFB_MEM_HOST, leaf_width=0, f32_mode=0, trsm_block
     return o
 
 
+def _column_major_lda(A: np.ndarray) -> Optional[int]:
+    """Leading dimension (elements) of a column-major view, or None when `A` is not one: rows must be contiguous
+    (stride == itemsize whenever m > 1) and the column stride a multiple of the itemsize with lda >= m (whenever
+    n > 1).  numpy reports arbitrary strides for length-1 axes, so only the axes that are walked are constrained --
+    but a single-column / single-row view of a larger array is still checked on the axis that is walked."""
+    m, n = A.shape
+    it = A.itemsize
+    if m > 1 and A.strides[0] != it:
+        return None
+    if n > 1:
+        s1 = A.strides[1]
+        if s1 <= 0 or s1 % it or s1 // it < max(m, 1):
+            return None
+        return s1 // it
+    return max(m, 1)
+
+
 def lu_(A, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check=True,
         blocksize: Optional[int] = None, threshold: Optional[int] = None, ctx: Optional[Context] = None,
         leaf_width: int = 0, f32_mode: int = 0, trsm_block: int = 0, gemm_path: int = 0,
@@ -406,9 +429,10 @@ def lu_(A, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check
     if A.dtype not in (np.float64, np.float32):
         raise TypeError(f"eltype {A.dtype} is not supported on the B200 path (Float64/Float32 only); no fallback")
     m, n = A.shape
-    if not (A.flags.f_contiguous or m <= 1 or n <= 1) or not A.flags.writeable or not A.flags.aligned:
-        raise TypeError("lu_ factors in place and needs a writeable column-major (Fortran-ordered) array; "
-                        "use lu() to factor a copy of any layout")
+    lda = _column_major_lda(A)
+    if lda is None or not A.flags.writeable or not A.flags.aligned:
+        raise TypeError("lu_ factors in place and needs a writeable column-major array (unit row stride, "
+                        "column stride lda >= m); use lu() to factor a copy of any layout")
     mn = min(m, n)
     if ipiv is None:
         ipiv = np.empty(mn, dtype=np.int64) if piv else NotIPIV(mn)      # init_pivot, src/lu.jl:33-40
@@ -425,7 +449,6 @@ def lu_(A, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check
             raise ValueError(f"ipiv has length {ipiv.size}, expected min(m, n) = {mn}")
     ctx = ctx or default_context()
     info = C.c_int64(0)
-    lda = max(m, 1)
     opts = _make_opts(_lib.RFB_MEM_HOST, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot=not piv)
     ipiv_ptr = ipiv.ctypes.data if (isinstance(ipiv, np.ndarray) and mn) else 0
     ctx.lu_raw(A.ctypes.data if A.size else 0, m, n, lda, ipiv_ptr, C.addressof(info), A.dtype, opts)
@@ -443,11 +466,16 @@ def ldiv_(F: LU, B: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
         raise ValueError("ldiv_ needs a square factorization")
     if not isinstance(B, np.ndarray) or B.dtype != f.dtype or B.shape[0] != n or B.ndim not in (1, 2):
         raise TypeError("B must be a numpy vector/matrix with n rows and the factors' eltype")
-    if not ((B.ndim == 1 and B.flags.c_contiguous) or (B.ndim == 2 and (B.flags.f_contiguous or B.shape[1] == 1))) \
-            or not B.flags.writeable:
-        raise TypeError("ldiv_ overwrites B and needs a writeable column-major array")
-    if not f.flags.f_contiguous:
+    if B.ndim == 1:
+        ldb = max(n, 1) if (n <= 1 or B.strides[0] == B.itemsize) else None
+    else:
+        ldb = _column_major_lda(B)
+    if ldb is None or not B.flags.writeable:
+        raise TypeError("ldiv_ overwrites B and needs a writeable column-major array (unit row stride)")
+    ldf = _column_major_lda(f)
+    if ldf is None:
         f = np.asfortranarray(f)
+        ldf = max(n, 1)
     nrhs = 1 if B.ndim == 1 else B.shape[1]
     # NotIPIV: both legs are plain triangular solves, no interchanges (src/lu.jl:60-64)
     ipiv = None if isinstance(F.ipiv, NotIPIV) else np.ascontiguousarray(F.ipiv, dtype=np.int64)
@@ -455,9 +483,9 @@ def ldiv_(F: LU, B: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
     lib = ctx._lib
     fn = lib.rfb_solve_f64 if f.dtype == np.float64 else lib.rfb_solve_f32
     opts = _make_opts(_lib.RFB_MEM_HOST)
-    ctx._check(fn(ctx.handle, C.c_void_p(f.ctypes.data), n, max(n, 1),
+    ctx._check(fn(ctx.handle, C.c_void_p(f.ctypes.data), n, ldf,
                   C.c_void_p(ipiv.ctypes.data) if ipiv is not None else None,
-                  C.c_void_p(B.ctypes.data), nrhs, max(n, 1), C.byref(opts)))
+                  C.c_void_p(B.ctypes.data), nrhs, ldb, C.byref(opts)))
     return B
 
 

@@ -181,6 +181,8 @@ int lu_range(rfb_ctx *ctx, T *A_root, int64_t m, int64_t lda, int64_t c0, int64_
     if (!A_root || !ipiv || !info) return ctx->fail(RFB_ERR_ARG, "rfb_lu_range: null pointer");
     if (c0 < 0 || n < 0 || c0 + n > m || lda < m) return ctx->fail(RFB_ERR_ARG, "rfb_lu_range: bad range/lda");
     if (n == 0) return RFB_OK;
+    if (opts && opts->no_pivot)
+        return ctx->fail(RFB_ERR_UNSUPPORTED, "rfb_lu_range: pivot = Val(false) is not distributed (use rfb_lu_* with no_pivot)");
     RFB_CUDA(ctx, cudaSetDevice(ctx->device));
     LuPlan plan;
     plan.opts = opts;
@@ -524,8 +526,18 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     cudaPointerAttributes pattr;
     const bool pinned = cudaPointerGetAttributes(&pattr, A) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    RFB_TRY(lu_device<T>(ctx, dA, m, n, ldd, nopiv ? nullptr : ctx->d_ipiv, ctx->d_info, opts, &evs, &bounds,
-                         (pinned && m >= n) ? A : nullptr, lda, &early_rows));
+    {
+        const int rc = lu_device<T>(ctx, dA, m, n, ldd, nopiv ? nullptr : ctx->d_ipiv, ctx->d_info, opts, &evs, &bounds,
+                                    (pinned && m >= n) ? A : nullptr, lda, &early_rows);
+        if (rc != RFB_OK) {
+            // uploads from / early downloads into the caller's matrix may still be in flight: the library never keeps a
+            // host pointer past the call, so drain both streams before reporting the failure
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->stream);
+            cudaGetLastError();
+            return rc;
+        }
+    }
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
     // download what the early copies (rows [0, early_rows) of all columns) did not cover
     if (early_rows > 0) {
@@ -869,8 +881,8 @@ int rfb_host_alloc(rfb_ctx *ctx, void **host_ptr, size_t bytes) {
     }
     return RFB_OK;
 }
-int rfb_host_free(rfb_ctx *ctx, void *host_ptr) {
-    RFB_CHECK_CTX(ctx);
+int rfb_host_free(rfb_ctx *ctx, void *host_ptr) {   // ctx may be NULL (the block outlives its context)
+    if (!ctx) return cudaFreeHost(host_ptr) == cudaSuccess ? RFB_OK : RFB_ERR_CUDA;
     RFB_CUDA(ctx, cudaFreeHost(host_ptr));
     return RFB_OK;
 }

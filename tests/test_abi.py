@@ -134,3 +134,28 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(rfb200.RfbError) as ei:
         rfb200.Context(0)
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_lu_rejects_views_that_are_not_column_major():
+    """a single-column / single-row view with non-unit strides must not reach the library (it would read
+    and overwrite the parent's neighbouring elements).  The layout check runs before any context is created."""
+    import rfb200
+    bad = [np.zeros((5, 3))[:, 0:1],                      # m x 1 view of a C-ordered array: row stride 24
+           np.zeros((4, 6), order="F")[0:1, :].T,         # n x 1 with row stride 32
+           np.zeros((6, 6))[:, :],                        # C-ordered square
+           np.zeros((8, 8), order="F")[::2, :]]           # row stride 16
+    for a in bad:
+        with pytest.raises(TypeError):
+            rfb200.lu_(a)
+    ok = rfb200._column_major_lda
+    assert ok(np.zeros((5, 3), order="F")) == 5
+    assert ok(np.zeros((10, 6), order="F")[:8, :]) == 10       # lda > m view
+    assert ok(np.zeros((10, 6), order="F")[:8, 2:3]) == 8      # single column of an F array: contiguous
+    assert ok(np.zeros((4, 6), order="F")[0:1, :]) == 4        # 1 x n view: columns 4 elements apart
+    assert ok(np.zeros((5, 3))[:, 0:1]) is None
+    assert ok(np.zeros((0, 0), order="F")) == 1
+    f = rfb200.LU(np.zeros((3, 3), order="F"), np.arange(1, 4), 0)
+    with pytest.raises(TypeError):
+        rfb200.ldiv_(f, np.zeros((3, 4))[:, 1:2])              # B: m x 1 view with row stride 32
+    with pytest.raises(TypeError):
+        rfb200.ldiv_(f, np.zeros(6)[::2])                      # strided vector

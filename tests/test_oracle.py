@@ -114,3 +114,26 @@ def test_edge_cases():
     a[5, 0] = np.nan
     _, ipiv, _ = O.lu_c(a.copy(order="F"))
     assert ipiv[0] != 6
+
+
+JULIA_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "julia_golden.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(JULIA_GOLDEN),
+                    reason="tests/golden/julia_golden.npz absent: the Julia reference cannot run in this image "
+                           "(generate it with tests/golden/make_golden_julia.jl where Julia exists)")
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_oracle_matches_julia_reference(idx):
+    """Pins the oracle against outputs of the real RecursiveFactorization.lu! (src/lu.jl:97-130) on the golden inputs:
+    `F.ipiv` / `F.info` exact, `F.factors` within the reference's own bound (test/runtests.jl:19-20)."""
+    g = np.load(JULIA_GOLDEN)
+    name, m, n, dt, special = CASES[idx]
+    a0 = make_input(idx)
+    f, ipiv, info = O.lu_c(a0.copy(order="F"))
+    for tag in ("serial", "threaded"):
+        assert info == int(g[f"{name}.{tag}.info"][0])
+        assert np.array_equal(ipiv, g[f"{name}.{tag}.ipiv"])
+        if info == 0:
+            assert np.abs(f - g[f"{name}.{tag}.factors"]).max() <= ref_bound(max(m, n), a0.dtype)
+    fn, _, infon = O.lu_nopiv_c(a0.copy(order="F"))
+    assert infon == int(g[f"{name}.nopiv.info"][0])
