@@ -8,6 +8,7 @@
 //     K1 launch factors the whole leaf panel.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "rfb_internal.h"
 
@@ -25,6 +26,7 @@ namespace {
 
 struct LuPlan {
     int leaf;
+    int64_t rows = 0;      // row count of the root matrix (bound of every row an exchange list can name)
     bool pivot = true;     // false: pivot = Val(false) (src/lu.jl:27-65), no interchanges, negative info
     bool lists;            // K1 emits row-exchange lists and K2 consumes them (default)
     const rfb_opts *opts;
@@ -55,7 +57,7 @@ static int need_cols(rfb_ctx *ctx, LuPlan &plan, int64_t ncols) {
 template <typename T>
 int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv, int64_t k0, int64_t np,
             const LuPlan &plan) {
-    if (plan.lists) return rfb_launch_laswp_lists<T>(ctx, A, ncols, lda, k0, k0 + np);
+    if (plan.lists) return rfb_launch_laswp_lists<T>(ctx, A, ncols, lda, k0, k0 + np, plan.rows);
     return rfb_launch_laswp<T>(ctx, A, ncols, lda, ipiv + k0, np, k0);
 }
 
@@ -128,6 +130,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     plan.host_A = host_A;
     plan.host_lda = host_lda;
     plan.host_m = m;
+    plan.rows = m;
     plan.n_total = n;
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     plan.pivot = !(opts && opts->no_pivot);
@@ -186,6 +189,7 @@ int lu_range(rfb_ctx *ctx, T *A_root, int64_t m, int64_t lda, int64_t c0, int64_
     RFB_CUDA(ctx, cudaSetDevice(ctx->device));
     LuPlan plan;
     plan.opts = opts;
+    plan.rows = m;
     plan.leaf = (opts && opts->leaf_width > 0) ? opts->leaf_width : 64;
     if (plan.leaf != 8 && plan.leaf != 16 && plan.leaf != 32 && plan.leaf != 64)
         return ctx->fail(RFB_ERR_ARG, "leaf_width must be 8, 16, 32 or 64 (got %d)", plan.leaf);
@@ -210,7 +214,7 @@ int laswp_range(rfb_ctx *ctx, T *A_root, int64_t lda, int64_t col0, int64_t ncol
     if (use_lists) {
         if (ctx->perm_dst == nullptr || (size_t)k1 > ctx->perm_cap)
             return ctx->fail(RFB_ERR_ARG, "rfb_laswp_range: exchange lists missing");
-        return rfb_launch_laswp_lists<T>(ctx, A, ncols, lda, k0, k1);
+        return rfb_launch_laswp_lists<T>(ctx, A, ncols, lda, k0, k1, lda);
     }
     if (!ipiv) return ctx->fail(RFB_ERR_ARG, "rfb_laswp_range: null ipiv");
     return rfb_launch_laswp<T>(ctx, A, ncols, lda, ipiv + k0, k1 - k0, k0);
@@ -562,7 +566,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     *info = ctx->h_pinned[0];
     if ((unsigned int)ctx->h_pinned[1] != 0) {
         cudaMemset(&ctx->xchg->error_flag, 0, sizeof(unsigned int));   // report once, keep the context usable
-        return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+        return ctx->fail(RFB_ERR_INTERNAL, "device-side protocol error (flag set: 1 = panel exchange timed out, 2 = row-exchange lists incomplete)");
     }
     return RFB_OK;
 }
@@ -603,6 +607,12 @@ int rfb_create(rfb_ctx **out, int device) {
     RFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
     RFB_CUDA(ctx, cudaMalloc(&ctx->xchg, sizeof(RfbPanelXchg)));
     RFB_CUDA(ctx, cudaMemset(ctx->xchg, 0, sizeof(RfbPanelXchg)));
+    if (const char *e = getenv("RFB_LASWP_NET_MIN")) ctx->laswp_net_min = atoll(e);
+    if (const char *e = getenv("RFB_LASWP_NET_CAP")) ctx->laswp_net_cap = atoll(e);
+    RFB_CUDA(ctx, cudaMalloc(&ctx->net_meta, 64));
+    RFB_CUDA(ctx, cudaMemset(ctx->net_meta, 0, 64));
+    RFB_CUDA(ctx, cudaMalloc(&ctx->net_srcmap, sizeof(int) * 8192));
+    RFB_CUDA(ctx, cudaMalloc(&ctx->net_clist, sizeof(int) * 2 * 8192));
     RFB_CUDA(ctx, cudaMalloc(&ctx->d_info, 64));
     RFB_CUDA(ctx, cudaMemset(ctx->d_info, 0, 64));
     RFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_pinned, 64, cudaHostAllocDefault));
@@ -625,6 +635,9 @@ int rfb_destroy(rfb_ctx *ctx) {
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->up_events) cudaEventDestroy(e);
     if (ctx->xchg) cudaFree(ctx->xchg);
+    if (ctx->net_meta) cudaFree(ctx->net_meta);
+    if (ctx->net_srcmap) cudaFree(ctx->net_srcmap);
+    if (ctx->net_clist) cudaFree(ctx->net_clist);
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
     if (ctx->d_binfo) cudaFree(ctx->d_binfo);
@@ -913,7 +926,7 @@ int rfb_sync(rfb_ctx *ctx) {
     RFB_CUDA(ctx, cudaMemcpy(&flag, &ctx->xchg->error_flag, sizeof(flag), cudaMemcpyDeviceToHost));
     if (flag) {
         cudaMemset(&ctx->xchg->error_flag, 0, sizeof(unsigned int));       // report once, keep the context usable
-        return ctx->fail(RFB_ERR_INTERNAL, "panel exchange timed out on the device (error flag set)");
+        return ctx->fail(RFB_ERR_INTERNAL, "device-side protocol error (flag set: 1 = panel exchange timed out, 2 = row-exchange lists incomplete)");
     }
     return RFB_OK;
 }

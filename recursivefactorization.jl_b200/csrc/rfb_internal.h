@@ -71,6 +71,10 @@ struct rfb_ctx {
     int *perm_dst = nullptr, *perm_src = nullptr, *perm_width = nullptr;
     size_t perm_cap = 0;                  // columns the three arrays are sized for
     bool perm_external = false;           // arrays belong to the caller (rfb_perm_buffers)
+    // node-level row interchange (laswp.cu): net permutation of the chunk being applied
+    int *net_meta = nullptr, *net_srcmap = nullptr, *net_clist = nullptr;
+    int64_t laswp_net_min = 256;          // pivot ranges at least this long take the node-level path (env RFB_LASWP_NET_MIN)
+    int64_t laswp_net_cap = 0;            // pivots per chunk, 0 = kernel default (env RFB_LASWP_NET_CAP; tests shrink it)
 
     std::vector<cudaEvent_t> up_events;   // upload-chunk events of host-mode calls (reused)
 
@@ -190,7 +194,7 @@ int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m);
 // list-driven row interchange: applies the exchange lists of the panels covering pivots [k0, k1)
 // to the (rows >= k0) x ncols block whose first row is absolute row k0
 template <typename T>
-int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1);
+int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1, int64_t row_bound);
 template <typename T>
 int rfb_launch_laswp(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
                      int64_t npiv, int64_t ipiv_sub);

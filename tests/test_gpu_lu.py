@@ -256,3 +256,33 @@ def test_ldiv_solve(ctx, dtype, n, nrhs):
     xw = np.linalg.solve(a0.astype(np.float64), b.astype(np.float64))
     r = np.abs(a0.astype(np.float64) @ xs.astype(np.float64) - b.astype(np.float64)).max()
     assert r <= 1000 * n * eps * max(1.0, np.abs(xw).max()), r        # the reference's solve bound (runtests.jl:82)
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (1500, 1500)), (np.float64, (2100, 900)), (np.float32, (1300, 1700)),
+                                         (np.float64, (777, 777))])
+def test_node_level_laswp_paths_agree(ctx, dtype, shape, monkeypatch):
+    """K2 has two list-driven forms: per panel (laswp_list_kernel) and per node (compose the node's panels into the
+    net permutation, one pass per column: laswp_compose_kernel + laswp_net_kernel).  The same factorization run with
+    the node-level path forced everywhere AND chunked into tiny pivot ranges, with it disabled, and with the defaults
+    must give IDENTICAL factors and pivots (row interchanges move bits, they do not compute), equal to the oracle's."""
+    m, n = shape
+    a0 = rand_matrix(np.random.default_rng([31, m, n]), m, n, dtype)
+    F0 = rfb200.lu(a0, ctx=ctx)
+    results = []
+    for net_min, net_cap in ((64, 192), (1 << 30, 0), (64, 0)):
+        monkeypatch.setenv("RFB_LASWP_NET_MIN", str(net_min))
+        monkeypatch.setenv("RFB_LASWP_NET_CAP", str(net_cap))
+        c2 = rfb200.Context(ctx.device)
+        try:
+            results.append(rfb200.lu(a0, ctx=c2))
+        finally:
+            c2.close()
+    for Fi in results:
+        assert Fi.info == F0.info == 0
+        assert np.array_equal(Fi.ipiv, F0.ipiv)
+        assert np.array_equal(Fi.factors, F0.factors)
+    _, want_p, _ = O.lu_c(a0.copy(order="F"), threads=8)
+    if dtype == np.float64:
+        assert np.array_equal(F0.ipiv, want_p)
+    else:
+        assert_pivots_match(a0, F0.factors, F0.ipiv, want_p, strict=False)
