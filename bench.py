@@ -62,7 +62,7 @@ def hutchinson_residual(a0, factors, ipiv, nvec=8, seed=0):
     ux = np.triu(factors[:mn, :]) @ x
     lux = np.tril(factors[:, :mn], -1) @ ux
     lux[:mn] += ux
-    pax = a0[p, :] @ x
+    pax = (a0 @ x)[p]                  # P (A x): no permuted copy of the matrix
     return float(np.linalg.norm(pax - lux) / np.sqrt(nvec) / np.linalg.norm(a0))
 
 
@@ -232,7 +232,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def other_configs(ctx, rfb200):
+def other_configs(ctx, rfb200, skip_big=False):
     """Device-resident timings (CUDA events, best of 3 after a warm-up, matrix restored by an untimed copy) of the
     other single-GPU BASELINE.json configs and of the rows SURVEY.md section 8f widens into.  Informational: the
     headline `value` / `e2e` above are the 16384 x 16384 Float64 pivoted LU."""
@@ -248,7 +248,7 @@ def other_configs(ctx, rfb200):
                 best = t if best is None else min(best, t)
         return best
 
-    def lu_case(n, dtype, check=None, **opt):
+    def lu_case(n, dtype, check=None, residual=True, **opt):
         a = np.empty((n, n), dtype=dtype, order="F")
         fill_random(a)
         if opt.get("no_pivot"):
@@ -256,8 +256,13 @@ def other_configs(ctx, rfb200):
         src = rfb200.DeviceMatrix(ctx, n, n, dtype, lda=n); src.upload(a); ctx.sync()
         dst = rfb200.DeviceMatrix(ctx, n, n, dtype, lda=n)
         ms = timed(lambda: dst.lu(**opt), lambda: dst.copy_from(src))
+        if not residual:                      # 8.6 GB matrices: no host-side probe (the multi-GPU run reports one at this size)
+            info_h = np.zeros(1, dtype=np.int64)
+            ctx.d2h(info_h, dst.info_ptr); ctx.sync()
+            src.free(); dst.free()
+            return {"ms": round(ms, 3), "gflops": round(lu_flops(n) / ms / 1e6, 1), "info": int(info_h[0])}
         f, ipiv, info = dst.download()
-        res = hutchinson_residual(a.astype(np.float64), f.astype(np.float64),
+        res = hutchinson_residual(a.astype(np.float64, copy=False), f.astype(np.float64, copy=False),
                                   np.arange(1, n + 1) if opt.get("no_pivot") else ipiv, nvec=4)
         src.free(); dst.free()
         out = {"ms": round(ms, 3), "gflops": round(lu_flops(n) / ms / 1e6, 1), "info": info, "residual_fro_rel_est": res,
@@ -284,6 +289,9 @@ def other_configs(ctx, rfb200):
     out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5, opt-in mode)"] = \
         lu_case(8192, np.float32, check="lapack", f32_mode=1)
     out["16384x16384 Float64 LU, pivot = Val(false) (src/lu.jl:27-65)"] = lu_case(16384, np.float64, no_pivot=1)
+    if not skip_big:
+        out["32768x32768 Float64 LU with partial pivoting on ONE GPU (the N = 1 point of the multi-GPU strong-scaling series, "
+            "BASELINE config 4)"] = lu_case(32768, np.float64, residual=False)
     # butterfly transform: algorithmic bytes 2 * 8 * n^2
     n = 16384
     d = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
@@ -344,8 +352,6 @@ def run_ours(args, rank, world, local_rank):
     pristine.upload(host)
     ctx.sync()
 
-    dmma_peak = ctx.dmma_peak_tflops(20000)
-
     # ---- device-resident timing ---------------------------------------------------------------
     sampler = ClockSampler(local_rank)     # started before the warm-up: nvidia-smi needs ~0.5 s to come up
     sampler.start()
@@ -368,6 +374,10 @@ def run_ours(args, rank, world, local_rank):
     launches = ctx.launch_count() - launches0
     ms = max_over_ranks(sum(times) / len(times))
     value = world * lu_flops(n) / (ms * 1e-3) / 1e9
+
+    # FP64 tensor peak: register-only DMMA microbenchmark, taken right after the timed region (clocks already up;
+    # a cold first call has read 20 % low) as the best of two calls of 3 launches each
+    dmma_peak = max(ctx.dmma_peak_tflops(40000), ctx.dmma_peak_tflops(40000))
 
     # ---- correctness of what was just timed ---------------------------------------------------
     f, ipiv, info = work.download()
@@ -440,7 +450,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the other single-GPU BASELINE configs and the widened rows, device resident (not the headline) ----
     others = None
     if world == 1 and not args.skip_others:
-        others = other_configs(ctx, rfb200)
+        others = other_configs(ctx, rfb200, skip_big=args.skip_big)
 
     # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
     cpu = None
@@ -472,7 +482,9 @@ def run_ours(args, rank, world, local_rank):
 
 
 def run_ours_dist(args, rank, world, local_rank):
-    """N > 1: ONE matrix factored by all GPUs (1-D block-cyclic columns + NCCL panel broadcast)."""
+    """N > 1: ONE matrix factored by all GPUs (1-D block-cyclic columns + NCCL panel broadcast, C++ driver behind
+    rfb_mg_*).  torch.distributed (gloo, CPU tensors) is only the launcher-side plumbing: the 128-byte NCCL id, the
+    barriers around the timed region and the max over ranks."""
     import torch
     import torch.distributed as dist
 
@@ -481,62 +493,68 @@ def run_ours_dist(args, rank, world, local_rank):
 
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout; stdout carries ONE JSON line
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist.init_process_group("gloo")
     n = args.n if args.n else 32768
     nb = args.block
-    d = DistributedLU(n, np.float64, block=nb)
-    dev = d.ctx.device_info()
+
+    def exchange(mine):
+        box = [mine]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    d = DistributedLU(n, np.float64, block=nb, rank=rank, world=world, device=local_rank, exchange_id=exchange)
+    ctx = rfb200.Context(local_rank)           # page-locked host buffers, pristine device copies, the 1-GPU comparison run
+    dev = ctx.device_info()
 
     def gen(j):
         c0, w = block_range(j, n, nb)
         return np.asfortranarray(np.random.default_rng([12, j]).random((n, w)))
 
-    # pinned host copies of this rank's block columns (each block column is contiguous: lda = n)
-    host_in, host_out, slices = {}, {}, {}
+    # pinned host copies of this rank's block columns (each is contiguous: lda = n) and pristine device copies
+    host_in, host_out, pristine = {}, {}, {}
     for j in d.my_blocks:
         c0, w = block_range(j, n, nb)
-        t = torch.empty(n * w, dtype=torch.float64, pin_memory=True)
-        t.numpy()[:] = gen(j).reshape(-1, order="F")
-        host_in[j] = t
-        host_out[j] = torch.empty(n * w, dtype=torch.float64, pin_memory=True)
-        slices[j] = d.block_slice(j)
-    pristine = {j: host_in[j].to(d.device) for j in d.my_blocks}
+        host_in[j] = ctx.pinned_empty((n, w), np.float64)
+        host_in[j][...] = gen(j)
+        host_out[j] = ctx.pinned_empty((n, w), np.float64)
+        pristine[j] = ctx.malloc(n * w * 8)
+        ctx.h2d(pristine[j], host_in[j])
+    ctx.sync()
 
     def restore():
-        with torch.cuda.stream(d.stream):
-            d.L.zero_()
-            for j in d.my_blocks:
-                slices[j].copy_(pristine[j])
-
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        for j in d.my_blocks:
+            d.restore_block(j, pristine[j])
+        d.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.5)
     for _ in range(args.warmup):
         restore()
-        d.factor()
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches0 = d.ctx.launch_count()
-    times = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(args.steps):
-        restore()
-        torch.cuda.synchronize()
         dist.barrier()
-        e0.record(d.stream)
         d.factor()
-        e1.record(d.stream)
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
+        d.synchronize()
+    dist.barrier()
+    launches0 = d.stats()["launches"]
+    times = []
+    for _ in range(args.steps):
+        restore()                  # outside the timed region (the factorization is in place)
+        dist.barrier()
+        d.factor()
+        times.append(d.synchronize())      # CUDA events on the rank's compute stream around the whole schedule
     dist.barrier()
     clocks = sampler.stop()
-    launches = d.ctx.launch_count() - launches0
+    launches = d.stats()["launches"] - launches0
     ms = max_over_ranks(sum(times) / len(times))
     value = lu_flops(n) / (ms * 1e-3) / 1e9
     info = d.info()
@@ -551,49 +569,47 @@ def run_ours_dist(args, rank, world, local_rank):
     nvec = 4
     x = np.random.default_rng(0).integers(0, 2, size=(n, nvec)).astype(np.float64) * 2 - 1
     ux = np.zeros((n, nvec)); pax = np.zeros((n, nvec)); nrm2 = 0.0; lmax = 0.0
+    fac = {}
     for j in d.my_blocks:
         c0, w = block_range(j, n, nb)
-        f = d.get_block(j)
+        d.store_block_async(j, host_out[j])
+    d.synchronize()
+    for j in d.my_blocks:
+        c0, w = block_range(j, n, nb)
+        f = np.asarray(host_out[j])
         rows = np.arange(n)[:, None]; cols = np.arange(c0, c0 + w)[None, :]
         ux += np.where(rows <= cols, f, 0.0) @ x[c0:c0 + w]
-        a0 = gen(j)
+        a0 = np.asarray(host_in[j])
         pax += a0[perm, :] @ x[c0:c0 + w]
         nrm2 += float(np.sum(a0 * a0))
         lmax = max(lmax, float(np.abs(np.where(rows > cols, f, 0.0)).max()))
-    tux = torch.from_numpy(ux).cuda(); dist.all_reduce(tux); ux = tux.cpu().numpy()
+    ux = sum_over_ranks(ux)
     lux = np.zeros((n, nvec))
     for j in d.my_blocks:
         c0, w = block_range(j, n, nb)
-        f = d.get_block(j)
+        f = np.asarray(host_out[j])
         rows = np.arange(n)[:, None]; cols = np.arange(c0, c0 + w)[None, :]
         lf = np.where(rows > cols, f, 0.0)
         lf[np.arange(c0, c0 + w), np.arange(w)] = 1.0
         lux += lf @ ux[c0:c0 + w]
-    t = torch.from_numpy(np.concatenate([(pax - lux).reshape(-1), [nrm2, 0.0]])).cuda()
-    # sum the partial P A x - L (U x) contributions, then norms
-    dist.all_reduce(t)
-    r = t[:-2].cpu().numpy()
-    res = float(np.linalg.norm(r) / np.sqrt(nvec) / np.sqrt(float(t[-2])))
-    tl = torch.tensor([lmax], device="cuda"); dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    t = sum_over_ranks(np.concatenate([(pax - lux).reshape(-1), [nrm2, 0.0]]))
+    res = float(np.linalg.norm(t[:-2]) / np.sqrt(nvec) / np.sqrt(float(t[-2])))
+    lmax = max_over_ranks(lmax)
 
-    # ---- end to end: pinned host blocks -> GPUs -> factor -> pinned host blocks -------------------
+    # ---- end to end: pinned host blocks -> GPUs -> factor -> pinned host blocks (uploads pipelined behind the first blocks) ----
     e2e = None
     if not args.skip_e2e:
         et = []
         for it in range(1 + min(args.steps, 2)):
-            with torch.cuda.stream(d.stream):
-                d.L.zero_()
-            torch.cuda.synchronize()
+            d.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
-            with torch.cuda.stream(d.stream):
-                for j in d.my_blocks:
-                    slices[j].copy_(host_in[j], non_blocking=True)
+            for j in d.my_blocks:
+                d.set_block(j, host_in[j])             # async H2D on the copy stream; the schedule waits per block column
             d.factor()
-            with torch.cuda.stream(d.stream):
-                for j in d.my_blocks:
-                    host_out[j].copy_(slices[j], non_blocking=True)
-            torch.cuda.synchronize()
+            for j in d.my_blocks:
+                d.store_block_async(j, host_out[j])
+            d.synchronize()
             dist.barrier()
             if it > 0:
                 et.append(time.perf_counter() - t0)
@@ -601,27 +617,58 @@ def run_ours_dist(args, rank, world, local_rank):
         e2e = {"value": lu_flops(n) / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8}
 
+    # ---- the same matrix on ONE GPU of this box (rank 0): pivot equality + the 1-GPU point of the strong-scaling series ----
+    single = None
+    if not args.skip_single and rank == 0:
+        a_full = np.empty((n, n), dtype=np.float64, order="F")
+        for j in range((n + nb - 1) // nb):
+            c0, w = block_range(j, n, nb)
+            a_full[:, c0:c0 + w] = host_in[j] if j in host_in else gen(j)
+        src = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n); src.upload(a_full); ctx.sync()
+        del a_full
+        work = rfb200.DeviceMatrix(ctx, n, n, np.float64, lda=n)
+        st = []
+        for it in range(3):
+            work.copy_from(src)
+            ctx.timer_start(); work.lu(); tms = ctx.timer_stop()
+            if it:
+                st.append(tms)
+        piv1 = np.empty(n, dtype=np.int64)
+        ctx.d2h(piv1, work.ipiv_ptr); ctx.sync()
+        s_ms = sum(st) / len(st)
+        single = {"pivots_equal_single_gpu": bool(np.array_equal(piv1, ipiv)), "strong_n1_ms": s_ms,
+                  "strong_n1_value": lu_flops(n) / (s_ms * 1e-3) / 1e9}
+        src.free(); work.free()
+    dist.barrier()
+
     if rank == 0:
+        checks = {"info": info, "residual_fro_rel_est": res, "bound_20_n_eps": 20 * n * float(np.finfo(np.float64).eps),
+                  "max_abs_L": lmax}
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{n}x{n} Float64 LU with partial pivoting, ONE matrix over {world} GPUs",
                        "input": "U[0,1) numpy default_rng([12, block]) per block column",
-                       "parallelism": f"1-D block-cyclic columns (block {nb}), owner-rooted NCCL broadcast of each factored "
-                                      f"block column + pivots + exchange lists, replicated L",
+                       "parallelism": f"1-D block-cyclic columns (block {nb}), owner-rooted ncclBroadcast of each factored block "
+                                      f"column + pivots + exchange lists on a dedicated stream, replicated L; C++ schedule (rfb_mg_*)",
                        "l2": f"matrix {n * n * 8 / 1e9:.1f} GB >> L2; restored from a device copy between steps (untimed)",
                        "device": dev},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "K4 trailing GEMM (FP64 DMMA)", "achieved": value / 1e3 / world,
                          "peak": None, "unit": "TFLOP/s per GPU (whole LU, not the kernel alone)", "frac": None, "traffic": None,
                          "note": "per-kernel roofline is reported by the 1-GPU run; here NCCL bytes per rank = "
-                                 f"{d.bcast_bytes / max(1, args.steps + args.warmup + (0 if args.skip_e2e else 1 + min(args.steps, 2))) / 1e9:.2f} GB per factorization"},
-            "cpu_baseline": None,
-            "checks": {"info": info, "residual_fro_rel_est": res, "bound_20_n_eps": 20 * n * float(np.finfo(np.float64).eps),
-                       "max_abs_L": float(tl.item())},
+                                 f"{d.stats()['bcast_bytes_per_rank'] / max(1, args.steps + args.warmup + (0 if args.skip_e2e else 1 + min(args.steps, 2))) / 1e9:.2f} GB per factorization"},
+            "cpu_baseline": None, "checks": checks,
         }
+        if single is not None:
+            checks["pivots_equal_single_gpu"] = single["pivots_equal_single_gpu"]
+            line["strong_n1_value"] = single["strong_n1_value"]
+            line["strong_n1_ms"] = single["strong_n1_ms"]
+            line["strong_scaling_efficiency_vs_in_run_n1"] = value / single["strong_n1_value"] / world
         print(json.dumps(line))
+    d.close()
+    ctx.close()
     dist.destroy_process_group()
 
 
@@ -637,6 +684,8 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-others", action="store_true", help="skip the informational other_configs block")
+    ap.add_argument("--skip-big", action="store_true", help="1 GPU: skip the 32768^2 single-GPU entry of other_configs")
+    ap.add_argument("--skip-single", action="store_true", help="multi-GPU: skip the in-run 1-GPU factorization of the same matrix")
     ap.add_argument("--check-pivots", dest="check_pivots", action="store_true", default=True,
                     help="compare the pivot vector of the timed factorization with LAPACK dgetrf (default: on)")
     ap.add_argument("--no-check-pivots", dest="check_pivots", action="store_false")

@@ -197,6 +197,50 @@ int rfb_copy2d(rfb_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, 
 /* enqueue on a caller-provided CUDA stream (e.g. torch's current stream); NULL restores the own one */
 int rfb_set_stream(rfb_ctx *ctx, void *cuda_stream);
 
+/* ---- multi-GPU whole path (SURVEY.md section 8b "rfb_lu_f64_mg", section 8e; BASELINE config "32768x32768 ... across 8xB200") ----
+ * ONE n x n matrix factored by G GPUs of one node: block columns of width `block` distributed 1-D block-cyclic (block column
+ * J on rank J mod G), each factored block column + its pivots broadcast from its owner with ncclBroadcast, L replicated.
+ * The schedule is C++ inside the library (csrc/rfb_mg.cu); libnccl is loaded with dlopen on first use.
+ *
+ * Two ways in:
+ *   one process, G devices (what a Julia caller of `lu!` uses; src/lu.jl:97-130 is the call this replaces):
+ *       rfb_mg_create_all(&mg, G, devices ( NULL = 0..G-1 ));
+ *       rfb_mg_lu_f64(mg, A_host, n, lda, ipiv, &info, block ( 0 = 512 ));      // upload, factor, download; A, ipiv, info as rfb_lu_f64
+ *       rfb_mg_destroy(mg);                    (rfb_lu_f64_mg = the three calls in one, pays the NCCL start-up every time)
+ *   one process per GPU (torchrun-style launchers; rank 0 makes the id and the launcher's own transport distributes it):
+ *       rfb_mg_unique_id(id128);  rfb_mg_create_rank(&mg, device, rank, nranks, id128);
+ *       rfb_mg_setup(mg, n, block, is_f32);  rfb_mg_load_block(mg, 0, j, src, ld, kind) for the owned block columns;
+ *       rfb_mg_factor(mg);  rfb_mg_sync(mg, &ms);  rfb_mg_store_block / rfb_mg_get_pivots / rfb_mg_get_info.
+ * `lr` is the LOCAL rank index (0..G-1 in a one-process handle, always 0 in a per-GPU handle).  Only square matrices.
+ */
+typedef struct rfb_mg rfb_mg;
+int rfb_mg_unique_id(void *id128);                                   /* ncclGetUniqueId: 128 bytes                      */
+int rfb_mg_create_rank(rfb_mg **out, int device, int rank, int nranks, const void *id128);
+int rfb_mg_create_all(rfb_mg **out, int ngpus, const int *devices);
+int rfb_mg_destroy(rfb_mg *mg);
+const char *rfb_mg_last_error(rfb_mg *mg);
+int rfb_mg_setup(rfb_mg *mg, int64_t n, int64_t block, int is_f32);  /* (re)allocates replica + own block columns       */
+int rfb_mg_local_ranks(rfb_mg *mg, int *count, int *world);
+int rfb_mg_rank_ctx(rfb_mg *mg, int lr, rfb_ctx **ctx, int *global_rank);   /* the rank's single-GPU context (same device) */
+int rfb_mg_block_ptr(rfb_mg *mg, int lr, int64_t j, void **dev_ptr); /* owned block column j: n x w, leading dimension n */
+/* copy block column j in (src_kind 0: host memory, 1: device memory) on the rank's copy stream; the factorization waits for it */
+int rfb_mg_load_block(rfb_mg *mg, int lr, int64_t j, const void *src, int64_t ld, int src_kind);
+int rfb_mg_store_block(rfb_mg *mg, int lr, int64_t j, void *dst_host, int64_t ld);   /* after the factorization, async       */
+int rfb_mg_factor(rfb_mg *mg);                 /* runs the schedule on every local rank; returns when all of it is enqueued */
+int rfb_mg_sync(rfb_mg *mg, float *ms);        /* waits; *ms = device time of the last factorization, max over local ranks  */
+int rfb_mg_get_pivots(rfb_mg *mg, int64_t *ipiv_host);               /* n pivots, 1-based global rows (every rank holds all) */
+int rfb_mg_get_info(rfb_mg *mg, int64_t *info);                      /* global info (collective in per-GPU handles)         */
+int rfb_mg_stats(rfb_mg *mg, int64_t *bcast_bytes_per_rank, int64_t *launches);
+int rfb_mg_lu_f64(rfb_mg *mg, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block);
+int rfb_mg_lu_f32(rfb_mg *mg, float *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block);
+int rfb_lu_f64_mg(const int *devices, int ngpus, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
+                  int64_t block);
+int rfb_lu_f32_mg(const int *devices, int ngpus, float *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,
+                  int64_t block);
+/* dry run of one rank's schedule (no GPU, no NCCL), 5 int64 per operation -- see csrc/rfb_mg.cu; used by the CPU tests, which
+ * replay it with the oracle's kernels over gloo and compare with the oracle's own LU */
+int rfb_mg_trace(int64_t n, int64_t block, int rank, int world, int64_t *ops, int64_t cap, int64_t *count);
+
 /* ---- host-driver trace (no GPU needed) -------------------------------------------------------------------
  * Runs the host recursion of rfb_lu_* (twin of src/lu.jl:97-156 and :189-263) for an m x n matrix WITHOUT launching
  * anything and returns the sequence of operations it would enqueue, 8 int64 per operation:

@@ -393,6 +393,8 @@ def _column_major_lda(A: np.ndarray) -> Optional[int]:
     but a single-column / single-row view of a larger array is still checked on the axis that is walked."""
     m, n = A.shape
     it = A.itemsize
+    if m == 0 or n == 0:
+        return max(m, 1)                    # nothing is read or written
     if m > 1 and A.strides[0] != it:
         return None
     if n > 1:

@@ -78,6 +78,27 @@ SIGNATURES = {
     "rfb_perm_buffers": (_int, [_p, _p, _p, _p, _i64]),
     "rfb_copy2d": (_int, [_p, _p, C.c_size_t, _p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "rfb_set_stream": (_int, [_p, _p]),
+    "rfb_mg_unique_id": (_int, [_p]),
+    "rfb_mg_create_rank": (_int, [C.POINTER(_p), _int, _int, _int, _p]),
+    "rfb_mg_create_all": (_int, [C.POINTER(_p), _int, C.POINTER(_int)]),
+    "rfb_mg_destroy": (_int, [_p]),
+    "rfb_mg_last_error": (C.c_char_p, [_p]),
+    "rfb_mg_setup": (_int, [_p, _i64, _i64, _int]),
+    "rfb_mg_local_ranks": (_int, [_p, C.POINTER(_int), C.POINTER(_int)]),
+    "rfb_mg_rank_ctx": (_int, [_p, _int, C.POINTER(_p), C.POINTER(_int)]),
+    "rfb_mg_block_ptr": (_int, [_p, _int, _i64, C.POINTER(_p)]),
+    "rfb_mg_load_block": (_int, [_p, _int, _i64, _p, _i64, _int]),
+    "rfb_mg_store_block": (_int, [_p, _int, _i64, _p, _i64]),
+    "rfb_mg_factor": (_int, [_p]),
+    "rfb_mg_sync": (_int, [_p, C.POINTER(C.c_float)]),
+    "rfb_mg_get_pivots": (_int, [_p, _p]),
+    "rfb_mg_get_info": (_int, [_p, C.POINTER(_i64)]),
+    "rfb_mg_stats": (_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "rfb_mg_lu_f64": (_int, [_p, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),
+    "rfb_mg_lu_f32": (_int, [_p, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),
+    "rfb_lu_f64_mg": (_int, [C.POINTER(_int), _int, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),
+    "rfb_lu_f32_mg": (_int, [C.POINTER(_int), _int, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),
+    "rfb_mg_trace": (_int, [_i64, _i64, _int, _int, _p, _i64, C.POINTER(_i64)]),
     "rfb_malloc": (_int, [_p, C.POINTER(_p), C.c_size_t]),
     "rfb_free": (_int, [_p, _p]),
     "rfb_host_alloc": (_int, [_p, C.POINTER(_p), C.c_size_t]),

@@ -262,8 +262,8 @@ static int launch_net(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int abs_ro
     constexpr size_t smem = sizeof(T) * (size_t)CPB * GS * VPT;
     auto kern = laswp_net_kernel<T, THREADS, GS, VPT>;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
-    kern<<<(unsigned int)((ncols + CPB - 1) / CPB), THREADS, smem, ctx->stream>>>(A, ncols, lda, abs_row0, ctx->net_meta,
-                                                                                 ctx->net_srcmap, ctx->net_clist);
+    kern<<<(unsigned int)((ncols + CPB - 1) / CPB), THREADS, smem, ctx->stream>>>(A, ncols, lda, abs_row0, ctx->net_meta(),
+                                                                                 ctx->net_srcmap(), ctx->net_clist());
     RFB_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return RFB_OK;
@@ -277,7 +277,7 @@ int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64
     const int64_t np = k1 - k0;
     const int64_t cap = ctx->laswp_net_cap > 0 && ctx->laswp_net_cap <= kNetCap ? ctx->laswp_net_cap : kNetCap;
     RfbLaunchScope scope(ctx, RFB_KC_LASWP, 4.0 * sizeof(T) * (double)np * (double)ncols);
-    if (np >= ctx->laswp_net_min && ctx->net_meta != nullptr && row_bound > k0 && row_bound - k0 <= kNetMaxRows) {
+    if (np >= ctx->laswp_net_min && ctx->net_meta() != nullptr && row_bound > k0 && row_bound - k0 <= kNetMaxRows) {
         // node-level path: compose the panels' lists into the net permutation, then one pass per column
         const int64_t rounds = np <= cap ? 1 : (np + (cap - RFB_MAX_NB) - 1) / (cap - RFB_MAX_NB);
         const int64_t chunk = np < cap ? np : cap;                // upper bound of a chunk's pivot count
@@ -285,8 +285,8 @@ int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64
         RFB_TRY(rfb_ensure_smem(ctx, (const void *)laswp_compose_kernel, sizeof(int) * (size_t)kNetMaxRows));
         for (int64_t r = 0; r < rounds; ++r) {
             laswp_compose_kernel<<<1, kComposeThreads, csmem, ctx->stream>>>(ctx->perm_dst, ctx->perm_src, ctx->perm_width, (int)k0,
-                                                                            (int)k1, (int)row_bound, (int)cap, r == 0 ? 1 : 0, ctx->net_meta,
-                                                                            ctx->net_srcmap, ctx->net_clist, &ctx->xchg->error_flag);
+                                                                            (int)k1, (int)row_bound, (int)cap, r == 0 ? 1 : 0, ctx->net_meta(),
+                                                                            ctx->net_srcmap(), ctx->net_clist(), &ctx->xchg->error_flag);
             RFB_CUDA(ctx, cudaGetLastError());
             ctx->launches++;
             int rc;

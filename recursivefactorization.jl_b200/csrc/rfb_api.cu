@@ -609,10 +609,12 @@ int rfb_create(rfb_ctx **out, int device) {
     RFB_CUDA(ctx, cudaMemset(ctx->xchg, 0, sizeof(RfbPanelXchg)));
     if (const char *e = getenv("RFB_LASWP_NET_MIN")) ctx->laswp_net_min = atoll(e);
     if (const char *e = getenv("RFB_LASWP_NET_CAP")) ctx->laswp_net_cap = atoll(e);
-    RFB_CUDA(ctx, cudaMalloc(&ctx->net_meta, 64));
-    RFB_CUDA(ctx, cudaMemset(ctx->net_meta, 0, 64));
-    RFB_CUDA(ctx, cudaMalloc(&ctx->net_srcmap, sizeof(int) * 8192));
-    RFB_CUDA(ctx, cudaMalloc(&ctx->net_clist, sizeof(int) * 2 * 8192));
+    for (int l = 0; l < rfb_ctx::kLanes; ++l) {
+        RFB_CUDA(ctx, cudaMalloc(&ctx->net_meta_[l], 64));
+        RFB_CUDA(ctx, cudaMemset(ctx->net_meta_[l], 0, 64));
+        RFB_CUDA(ctx, cudaMalloc(&ctx->net_srcmap_[l], sizeof(int) * 8192));
+        RFB_CUDA(ctx, cudaMalloc(&ctx->net_clist_[l], sizeof(int) * 2 * 8192));
+    }
     RFB_CUDA(ctx, cudaMalloc(&ctx->d_info, 64));
     RFB_CUDA(ctx, cudaMemset(ctx->d_info, 0, 64));
     RFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_pinned, 64, cudaHostAllocDefault));
@@ -635,9 +637,11 @@ int rfb_destroy(rfb_ctx *ctx) {
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->up_events) cudaEventDestroy(e);
     if (ctx->xchg) cudaFree(ctx->xchg);
-    if (ctx->net_meta) cudaFree(ctx->net_meta);
-    if (ctx->net_srcmap) cudaFree(ctx->net_srcmap);
-    if (ctx->net_clist) cudaFree(ctx->net_clist);
+    for (int l = 0; l < rfb_ctx::kLanes; ++l) {
+        if (ctx->net_meta_[l]) cudaFree(ctx->net_meta_[l]);
+        if (ctx->net_srcmap_[l]) cudaFree(ctx->net_srcmap_[l]);
+        if (ctx->net_clist_[l]) cudaFree(ctx->net_clist_[l]);
+    }
     if (ctx->d_info) cudaFree(ctx->d_info);
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
     if (ctx->d_binfo) cudaFree(ctx->d_binfo);

@@ -72,8 +72,14 @@ struct rfb_ctx {
     size_t perm_cap = 0;                  // columns the three arrays are sized for
     bool perm_external = false;           // arrays belong to the caller (rfb_perm_buffers)
     // node-level row interchange (laswp.cu): net permutation of the chunk being applied
-    int *net_meta = nullptr, *net_srcmap = nullptr, *net_clist = nullptr;
-    int64_t laswp_net_min = 256;          // pivot ranges at least this long take the node-level path (env RFB_LASWP_NET_MIN)
+    // (one set per lane: the multi-GPU driver runs interchanges on its compute stream and on its replica stream at once)
+    static constexpr int kLanes = 2;
+    int lane = 0;
+    int *net_meta_[kLanes] = {nullptr, nullptr}, *net_srcmap_[kLanes] = {nullptr, nullptr}, *net_clist_[kLanes] = {nullptr, nullptr};
+    int *net_meta() const { return net_meta_[lane]; }
+    int *net_srcmap() const { return net_srcmap_[lane]; }
+    int *net_clist() const { return net_clist_[lane]; }
+    int64_t laswp_net_min = 512;          // pivot ranges at least this long take the node-level path (env RFB_LASWP_NET_MIN)
     int64_t laswp_net_cap = 0;            // pivots per chunk, 0 = kernel default (env RFB_LASWP_NET_CAP; tests shrink it)
 
     std::vector<cudaEvent_t> up_events;   // upload-chunk events of host-mode calls (reused)

@@ -1,0 +1,962 @@
+// rfb_mg.cu -- multi-GPU recursive LU behind the C ABI (SURVEY.md section 8b "rfb_lu_f64_mg", section 8e).
+//
+// The reference has no distributed path; this is the same Toledo recursion (src/lu.jl:189-263) run over BLOCK
+// COLUMNS distributed 1-D block-cyclic over G GPUs of one node:
+//   * block column J (width nb) is owned by rank J mod G; a recursion node that is one block column is factored by its
+//     owner with the single-GPU path (reckernel! on the column range, rfb_lu_range), then the factored panel (rows below
+//     its diagonal block included) + its pivots + its row-exchange lists are broadcast from the owner with ncclBroadcast;
+//   * every rank keeps a full-size replica of L (valid where panels were received), so steps 2-4 of the recursion
+//     (row swaps :233, TRSM :235, Schur update :240) touch only columns the rank owns and need no communication;
+//     step 6 (:246, A21 <- P2 A21) is applied to the replica on every rank.
+//
+// What is different from round 1 (a Python schedule on one stream per rank):
+//   * the schedule is C++, behind the C ABI; no torch / Python in the product path.  Two ways in: one process with G
+//     devices (rfb_mg_create_all: ncclCommInitRank per device inside one group, one host thread per device) -- what a
+//     Julia caller of lu! uses -- or one process per GPU (rfb_mg_create_rank with a shared ncclUniqueId) -- what
+//     torchrun / bench.py uses.  libnccl is loaded with dlopen, so the single-GPU library has no NCCL dependency.
+//   * communication has its own (high-priority) stream per rank: pack -> ncclBroadcast -> unpack -> replica swaps run
+//     there, ordered against the compute stream by events, so a rank's GEMMs overlap its own broadcasts.
+//   * updates are per (node, block column) tasks and are ordered by NEED, not by recursion order: the task list of an
+//     owned block column is "all ancestors' updates, top-down, then factor".  A host scheduler per rank keeps the
+//     compute stream fed: when everything the next owned block column waits for has ARRIVED (event query), its
+//     remaining updates + its factorization go out back to back (the critical path); otherwise a bounded slice
+//     (~0.3 ms) of the most urgent update whose inputs have arrived.  Long GEMMs are cut into one-wave pieces (rows and
+//     k) so the critical path never waits for more than two slices.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdlib>
+#include <dlfcn.h>
+#include <mutex>
+#include <thread>
+
+#include <nccl.h>
+
+#include "rfb_internal.h"
+
+namespace {
+
+// ---- libnccl, loaded on first use ---------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("RFB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm) continue;
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) { api.error = std::string("cannot load libnccl: ") + dlerror(); return; }
+        auto sym = [&](const char *n) { return dlsym(api.handle, n); };
+#define RFB_NCCL_SYM(field, name)                                                  \
+        api.field = reinterpret_cast<decltype(api.field)>(sym(name));              \
+        if (!api.field && api.error.empty()) api.error = std::string("libnccl lacks ") + name;
+        RFB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        RFB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        RFB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        RFB_NCCL_SYM(CommAbort, "ncclCommAbort")
+        RFB_NCCL_SYM(Broadcast, "ncclBroadcast")
+        RFB_NCCL_SYM(AllReduce, "ncclAllReduce")
+        RFB_NCCL_SYM(GroupStart, "ncclGroupStart")
+        RFB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        RFB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef RFB_NCCL_SYM
+        api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(sym("ncclCommInitRankConfig"));   // optional
+    });
+    return &api;
+}
+
+// ---- the block-column recursion tree (pure host logic; shared by the GPU run and the dry-run trace) ------------------------
+struct MgNode {
+    int b0, nbk, nb1;     // blocks [b0, b0 + nbk), left half [b0, b0 + nb1)
+};
+
+struct MgPlan {
+    int64_t n = 0, nb = 0;
+    int nblk = 0, world = 1;
+    std::vector<MgNode> nodes;
+    std::vector<std::vector<int>> anc;       // anc[j]: nodes (top-down) whose RIGHT half holds block j -> the updates block j receives
+    std::vector<std::vector<int>> ends_at;   // ends_at[e]: nodes whose last block is e, innermost first -> A21 <- P2 A21 (:246) points
+
+    int64_t col0(int b) const { return (int64_t)b * nb; }
+    int64_t width(int b) const { return std::min<int64_t>(n, (int64_t)(b + 1) * nb) - (int64_t)b * nb; }
+    int owner(int b) const { return b % world; }
+
+    void build_rec(int b0, int nbk) {
+        if (nbk <= 1) return;
+        const int nb1 = (nbk + 1) / 2;                 // block analogue of nsplit (src/lu.jl:158-162)
+        const int id = (int)nodes.size();
+        nodes.push_back({b0, nbk, nb1});
+        for (int j = b0 + nb1; j < b0 + nbk; ++j) anc[j].push_back(id);
+        build_rec(b0, nb1);
+        build_rec(b0 + nb1, nbk - nb1);
+        ends_at[b0 + nbk - 1].push_back(id);           // post-order: inner nodes are pushed first
+    }
+    void build(int64_t n_, int64_t nb_, int world_) {
+        n = n_; nb = nb_; world = world_;
+        nblk = (int)((n + nb - 1) / nb);
+        nodes.clear();
+        anc.assign(nblk, {});
+        ends_at.assign(nblk, {});
+        build_rec(0, nblk);
+    }
+};
+
+enum MgTraceCode { MG_T_UPDATE = 1, MG_T_FACTOR = 2, MG_T_BCAST = 3, MG_T_SWAP_LEFT = 4 };
+
+// One launch-level operation of an update task.
+struct MgOp {
+    int kind;                 // 0 row interchange, 1 TRSM diagonal block, 2 GEMM piece
+    char *p0, *p1, *p2;       // swap: block;  trsm: L, B;  gemm: C, A, B
+    int64_t a, b, c;          // swap: ncols, k0, k1;  trsm: k, nrhs;  gemm: m, n, k
+    double est_us;
+};
+
+struct MgRank;
+
+}  // namespace
+
+struct rfb_mg {
+    std::vector<MgRank *> ranks;       // local ranks (G in one-process mode, 1 in one-process-per-GPU mode)
+    int world = 1;
+    bool all_mode = false;
+    std::string last_error;
+    int64_t n = 0, nb = 0;
+    bool f32 = false;
+    float last_ms = 0;
+};
+
+namespace {
+
+struct MgRank {
+    rfb_mg *mg = nullptr;
+    int rank = 0, world = 1, device = 0;
+    rfb_ctx *ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    cudaStream_t s_comp = nullptr, s_L = nullptr, s_copy = nullptr;
+    MgPlan plan;
+    bool f32 = false;
+    size_t es = 8;
+    std::vector<int> own;
+    std::vector<int64_t> lcol;
+    int64_t ncl = 0;
+    char *A = nullptr, *L = nullptr, *stage = nullptr;
+    int64_t *ipiv = nullptr, *info = nullptr;
+    int *pdst = nullptr, *psrc = nullptr, *pwidth = nullptr;
+    std::vector<cudaEvent_t> ev_blk, ev_fact, ev_up;
+    std::vector<char> up_pending;
+    cudaEvent_t ev_sent = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_final = nullptr, ev_chunk[2] = {nullptr, nullptr};
+    rfb_opts opts = {};
+    int64_t kmax = 2048;            // bulk GEMM pieces: at most this many inner columns per launch (0 = never split k)
+    double slice_us = 250.0;
+    int status = RFB_OK;
+    std::string error;
+    int64_t bcast_bytes = 0;
+    // dry run
+    bool dry = false;
+    std::vector<int64_t> *trace = nullptr;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        error = buf;
+        status = code;
+        return code;
+    }
+    char *Aj(int64_t r, int64_t lc) const { return A + ((size_t)r + (size_t)lc * (size_t)plan.n) * es; }
+    char *Lp(int64_t r, int64_t c) const { return L + ((size_t)r + (size_t)c * (size_t)plan.n) * es; }
+    void rec(int code, int64_t a, int64_t b, int64_t c, int64_t d) {
+        trace->push_back(code); trace->push_back(a); trace->push_back(b); trace->push_back(c); trace->push_back(d);
+    }
+};
+
+#define MG_CUDA(r, call)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return (r)->fail(RFB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+#define MG_NCCL(r, call)                                                                                       \
+    do {                                                                                                       \
+        ncclResult_t e__ = (call);                                                                             \
+        if (e__ != ncclSuccess)                                                                                \
+            return (r)->fail(RFB_ERR_NCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, nccl_api()->GetErrorString(e__)); \
+    } while (0)
+#define MG_TRY(r, expr)                                                                       \
+    do {                                                                                      \
+        int rc__ = (expr);                                                                    \
+        if (rc__ != RFB_OK) {                                                                 \
+            if ((r)->status == RFB_OK) (r)->fail(rc__, "%s", (r)->ctx ? (r)->ctx->last_error.c_str() : "error"); \
+            return rc__;                                                                      \
+        }                                                                                     \
+    } while (0)
+
+// ---- expansion of one update task U(node -> block j) into launch-level operations ----------------------------------------
+template <typename T>
+void emit_gemm(std::vector<MgOp> &ops, char *C, char *A, char *B, int64_t m, int64_t nn, int64_t k, int64_t lda, bool split,
+               int64_t kmax) {
+    if (m <= 0 || nn <= 0 || k <= 0) return;
+    const int64_t kstep = (split && kmax > 0) ? kmax : k;
+    const int64_t tiles_n = (nn + 127) / 128;
+    // one-wave pieces: ~128 tiles of 128 x 128 fit beside the communication kernel's CTAs on 148 SMs
+    const int64_t rstep = split ? 128 * std::max<int64_t>(1, 128 / tiles_n) : m;
+    for (int64_t k0 = 0; k0 < k; k0 += kstep) {
+        const int64_t kk = std::min(kstep, k - k0);
+        for (int64_t r0 = 0; r0 < m; r0 += rstep) {
+            const int64_t mr = std::min(rstep, m - r0);
+            MgOp o{};
+            o.kind = 2;
+            o.p0 = C + (size_t)r0 * sizeof(T);
+            o.p1 = A + ((size_t)r0 + (size_t)k0 * (size_t)lda) * sizeof(T);
+            o.p2 = B + (size_t)k0 * sizeof(T);
+            o.a = mr; o.b = nn; o.c = kk;
+            o.est_us = 4.0 + 2.0 * (double)mr * (double)nn * (double)kk / (sizeof(T) == 8 ? 26e6 : 60e6);
+            ops.push_back(o);
+        }
+    }
+}
+
+template <typename T>
+void emit_trsm(std::vector<MgOp> &ops, char *Lm, int64_t k, char *B, int64_t nrhs, int64_t lda, bool split, int64_t kmax) {
+    constexpr int64_t tb = 256;                              // the fused 256-row block solve (trsm.cu)
+    if (k <= tb) {
+        MgOp o{};
+        o.kind = 1; o.p0 = Lm; o.p1 = B; o.a = k; o.b = nrhs;
+        o.est_us = 8.0 + (double)k * 0.14 * (double)((nrhs + 4735) / 4736);
+        ops.push_back(o);
+        return;
+    }
+    int64_t k1 = ((k / 2 + tb - 1) / tb) * tb;               // same split rule as trsm_rec
+    if (k1 >= k) k1 = ((k - 1) / tb) * tb;
+    emit_trsm<T>(ops, Lm, k1, B, nrhs, lda, split, kmax);
+    emit_gemm<T>(ops, B + (size_t)k1 * sizeof(T), Lm + (size_t)k1 * sizeof(T), B, k - k1, nrhs, k1, lda, split, kmax);
+    emit_trsm<T>(ops, Lm + ((size_t)k1 + (size_t)k1 * (size_t)lda) * sizeof(T), k - k1, B + (size_t)k1 * sizeof(T), nrhs, lda, split, kmax);
+}
+
+template <typename T>
+int run_op(MgRank *r, const MgOp &o) {
+    rfb_ctx *ctx = r->ctx;
+    const int64_t lda = r->plan.n;
+    switch (o.kind) {
+        case 0: return rfb_launch_laswp_lists<T>(ctx, reinterpret_cast<T *>(o.p0), o.a, lda, o.b, o.c, r->plan.n);
+        case 1: return rfb_launch_trsm<T>(ctx, reinterpret_cast<const T *>(o.p0), o.a, reinterpret_cast<T *>(o.p1), o.b, lda, &r->opts);
+        default: return rfb_launch_gemm<T>(ctx, reinterpret_cast<T *>(o.p0), reinterpret_cast<const T *>(o.p1),
+                                           reinterpret_cast<const T *>(o.p2), o.a, o.b, o.c, lda, &r->opts);
+    }
+}
+
+// ---- the per-rank scheduler -----------------------------------------------------------------------------------------------
+template <typename T>
+struct MgSched {
+    MgRank *r;
+    const MgPlan &P;
+    int comm_cursor = 0;                       // next block whose publish (+ node-end swaps) goes onto the replica stream
+    std::vector<char> factored;                // own blocks: factorization enqueued
+    std::vector<int> next_task;                // own blocks: index into anc[j] of the next update task
+    std::vector<std::vector<MgOp>> ops;        // own blocks: operations of the task in progress
+    std::vector<size_t> op_pos;
+    std::vector<char> touched;
+    int chunks = 0;
+
+    explicit MgSched(MgRank *rank) : r(rank), P(rank->plan) {
+        factored.assign(P.nblk, 0);
+        next_task.assign(P.nblk, 0);
+        ops.assign(P.nblk, {});
+        op_pos.assign(P.nblk, 0);
+        touched.assign(P.nblk, 0);
+    }
+
+    int dep_block(int node) const { return P.nodes[node].b0 + P.nodes[node].nb1 - 1; }   // last block of the node's left half
+    bool recorded(int blk) const { return comm_cursor > blk; }
+    bool arrived(int blk) const {
+        if (!recorded(blk)) return false;
+        if (r->dry) return true;
+        return cudaEventQuery(r->ev_blk[blk]) == cudaSuccess;
+    }
+
+    // ---- replica stream -----------------------------------------------------------------------------------------------
+    int publish(int b) {
+        const int root = P.owner(b);
+        const int64_t c0 = P.col0(b), w = P.width(b), rows = P.n - c0;
+        if (r->dry) { r->rec(MG_T_BCAST, b, root, c0, w); return RFB_OK; }
+        const size_t es = r->es;
+        const size_t pbytes = (size_t)rows * (size_t)w * es;
+        const size_t off_piv = pbytes, off_dst = pbytes + 8 * (size_t)w, off_src = pbytes + 16 * (size_t)w, off_w = pbytes + 24 * (size_t)w;
+        const size_t total = pbytes + 28 * (size_t)w;
+        cudaStream_t s = r->s_L;
+        if (r->rank == root) {
+            MG_CUDA(r, cudaStreamWaitEvent(s, r->ev_fact[b], 0));
+            if (P.world > 1) {
+                MG_CUDA(r, cudaMemcpy2DAsync(r->stage, rows * es, r->Aj(c0, r->lcol[b]), P.n * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->stage + off_piv, r->ipiv + c0, 8 * w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->stage + off_dst, r->pdst + 2 * c0, 8 * w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->stage + off_src, r->psrc + 2 * c0, 8 * w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->stage + off_w, r->pwidth + c0, 4 * w, cudaMemcpyDeviceToDevice, s));
+            }
+        }
+        if (P.world > 1) {
+            MG_NCCL(r, nccl_api()->Broadcast(r->stage, r->stage, total, ncclUint8, root, r->comm, s));
+            r->bcast_bytes += (int64_t)total;
+            if (r->rank == root) {       // the owner's next compute work must not take the SMs before its send has started
+                MG_CUDA(r, cudaEventRecord(r->ev_sent, s));
+                MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_sent, 0));
+            }
+            MG_CUDA(r, cudaMemcpy2DAsync(r->Lp(c0, c0), P.n * es, r->stage, rows * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
+            if (r->rank != root) {
+                MG_CUDA(r, cudaMemcpyAsync(r->ipiv + c0, r->stage + off_piv, 8 * w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->pdst + 2 * c0, r->stage + off_dst, 8 * w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->psrc + 2 * c0, r->stage + off_src, 8 * w, cudaMemcpyDeviceToDevice, s));
+                MG_CUDA(r, cudaMemcpyAsync(r->pwidth + c0, r->stage + off_w, 4 * w, cudaMemcpyDeviceToDevice, s));
+            }
+        } else {
+            MG_CUDA(r, cudaMemcpy2DAsync(r->Lp(c0, c0), P.n * es, r->Aj(c0, r->lcol[b]), P.n * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
+        }
+        return RFB_OK;
+    }
+
+    // src/lu.jl:246 for node `id`: pivots of its right half applied to its left half's columns (rows below the left half)
+    int swap_left(int id) {
+        const MgNode &N = P.nodes[id];
+        const int64_t c0 = P.col0(N.b0), n1 = (int64_t)N.nb1 * P.nb;
+        const int64_t k0 = c0 + n1, k1 = std::min<int64_t>(P.n, P.col0(N.b0 + N.nbk));
+        if (r->dry) { r->rec(MG_T_SWAP_LEFT, c0, n1, k0, k1); return RFB_OK; }
+        cudaStream_t s = r->s_L;
+        // every reader of this region on the compute stream precedes the factorization of this rank's last block of the node
+        int last_own = -1;
+        for (int j = N.b0 + N.nbk - 1; j >= N.b0; --j)
+            if (P.owner(j) == r->rank) { last_own = j; break; }
+        if (last_own >= 0) MG_CUDA(r, cudaStreamWaitEvent(s, r->ev_fact[last_own], 0));
+        rfb_ctx *ctx = r->ctx;
+        ctx->stream = s;
+        ctx->lane = 1;
+        int rc = rfb_launch_laswp_lists<T>(ctx, reinterpret_cast<T *>(r->Lp(k0, c0)), n1, P.n, k0, k1, P.n);
+        int first_own = -1, cnt = 0;
+        for (int j = N.b0; j < N.b0 + N.nb1; ++j)
+            if (P.owner(j) == r->rank) { if (first_own < 0) first_own = j; cnt++; }
+        if (rc == RFB_OK && cnt > 0)           // the rank's own copy of those columns (contiguous: local storage is in block order)
+            rc = rfb_launch_laswp_lists<T>(ctx, reinterpret_cast<T *>(r->Aj(k0, r->lcol[first_own])), (int64_t)cnt * P.nb, P.n, k0, k1, P.n);
+        ctx->stream = r->s_comp;
+        ctx->lane = 0;
+        MG_TRY(r, rc);
+        return RFB_OK;
+    }
+
+    int advance_comm() {
+        while (comm_cursor < P.nblk) {
+            const int b = comm_cursor;
+            if (P.owner(b) == r->rank && !factored[b]) break;
+            MG_TRY(r, publish(b));
+            for (int id : P.ends_at[b]) MG_TRY(r, swap_left(id));
+            if (!r->dry) MG_CUDA(r, cudaEventRecord(r->ev_blk[b], r->s_L));
+            comm_cursor++;
+        }
+        return RFB_OK;
+    }
+
+    // ---- compute stream -----------------------------------------------------------------------------------------------
+    void build_task(int j) {
+        const int id = P.anc[j][next_task[j]];
+        const MgNode &N = P.nodes[id];
+        const int64_t c0 = P.col0(N.b0), n1 = (int64_t)N.nb1 * P.nb, w = P.width(j), lc = r->lcol[j];
+        const bool split = next_task[j] + 1 < (int)P.anc[j].size();      // the lowest update runs on the critical path: whole launches
+        std::vector<MgOp> &v = ops[j];
+        v.clear();
+        op_pos[j] = 0;
+        MgOp s{};
+        s.kind = 0; s.p0 = r->Aj(c0, lc); s.a = w; s.b = c0; s.c = c0 + n1;
+        s.est_us = 6.0 + 32.0 * (double)n1 * (double)w / 2.5e6;
+        v.push_back(s);                                                                                  // :233
+        emit_trsm<T>(v, r->Lp(c0, c0), n1, r->Aj(c0, lc), w, P.n, split, r->kmax);                       // :235
+        emit_gemm<T>(v, r->Aj(c0 + n1, lc), r->Lp(c0 + n1, c0), r->Aj(c0, lc), P.n - c0 - n1, w, n1, P.n, split, r->kmax);   // :240
+    }
+
+    // enqueue operations of block j's current task until `budget_us` of estimated work is out (or the task ends)
+    int advance_task(int j, double budget_us) {
+        if (r->dry) {
+            const MgNode &N = P.nodes[P.anc[j][next_task[j]]];
+            r->rec(MG_T_UPDATE, P.col0(N.b0), (int64_t)N.nb1 * P.nb, j, 0);
+            next_task[j]++;
+            return RFB_OK;
+        }
+        if (ops[j].empty()) {
+            build_task(j);
+            if (!touched[j]) {
+                touched[j] = 1;
+                if (r->up_pending[j]) { MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_up[j], 0)); r->up_pending[j] = 0; }
+            }
+            MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_blk[dep_block(P.anc[j][next_task[j]])], 0));
+        }
+        double out = 0;
+        while (op_pos[j] < ops[j].size() && out < budget_us) {
+            const MgOp &o = ops[j][op_pos[j]++];
+            MG_TRY(r, run_op<T>(r, o));
+            out += o.est_us;
+        }
+        if (op_pos[j] >= ops[j].size()) { ops[j].clear(); next_task[j]++; }
+        return RFB_OK;
+    }
+
+    int factor(int j) {
+        const int64_t c0 = P.col0(j), w = P.width(j);
+        factored[j] = 1;
+        if (r->dry) { r->rec(MG_T_FACTOR, j, c0, w, 0); return RFB_OK; }
+        if (!touched[j]) {
+            touched[j] = 1;
+            if (r->up_pending[j]) { MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_up[j], 0)); r->up_pending[j] = 0; }
+        }
+        // the block lives at local column lcol[j]: shift the base so that (row c0, column c0) of the "root" view is it
+        char *root = r->A + ((size_t)(r->lcol[j] - c0) * (size_t)P.n) * r->es;   // (pointer arithmetic only; never dereferenced outside the block)
+        int rc;
+        if (sizeof(T) == 8) rc = rfb_lu_range_f64(r->ctx, reinterpret_cast<double *>(root), P.n, P.n, c0, w, r->ipiv, r->info, &r->opts);
+        else rc = rfb_lu_range_f32(r->ctx, reinterpret_cast<float *>(root), P.n, P.n, c0, w, r->ipiv, r->info, &r->opts);
+        MG_TRY(r, rc);
+        MG_CUDA(r, cudaEventRecord(r->ev_fact[j], r->s_comp));
+        return RFB_OK;
+    }
+
+    int chunks_in_flight() {
+        int c = 0;
+        for (int i = 0; i < 2; ++i)
+            if (chunks > i && cudaEventQuery(r->ev_chunk[(chunks - 1 - i) & 1]) != cudaSuccess) c++;
+        return c;
+    }
+
+    int run() {
+        using clock = std::chrono::steady_clock;
+        auto last_progress = clock::now();
+        size_t own_pos = 0;                                          // index into r->own of the next block to factor
+        while (true) {
+            MG_TRY(r, advance_comm());
+            while (own_pos < r->own.size() && factored[r->own[own_pos]]) own_pos++;
+            if (own_pos >= r->own.size()) {
+                if (comm_cursor >= P.nblk) break;
+                continue;                                             // only other ranks' blocks remain: advance_comm enqueues them all
+            }
+            const int jn = r->own[own_pos];
+            // critical path: everything block jn still waits for has arrived -> its remaining updates and its factorization, back to back
+            bool crit = true;
+            for (int t = next_task[jn]; t < (int)P.anc[jn].size() && crit; ++t) crit = arrived(dep_block(P.anc[jn][t]));
+            if (crit) {
+                while (next_task[jn] < (int)P.anc[jn].size()) MG_TRY(r, advance_task(jn, 1e30));
+                MG_TRY(r, factor(jn));
+                last_progress = clock::now();
+                continue;
+            }
+            // otherwise one bounded slice of the most urgent update whose inputs have arrived (at most two slices in flight)
+            int pick = -1;
+            for (size_t q = own_pos; q < r->own.size(); ++q) {
+                const int j = r->own[q];
+                if (next_task[j] < (int)P.anc[j].size() && arrived(dep_block(P.anc[j][next_task[j]]))) { pick = j; break; }
+            }
+            if (pick >= 0 && (r->dry || chunks_in_flight() < 2)) {
+                MG_TRY(r, advance_task(pick, r->slice_us));
+                if (!r->dry) { MG_CUDA(r, cudaEventRecord(r->ev_chunk[chunks & 1], r->s_comp)); chunks++; }
+                last_progress = clock::now();
+                continue;
+            }
+            if (r->dry) return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule cannot make progress (block %d)", jn);
+            if (std::chrono::duration<double>(clock::now() - last_progress).count() > 60.0)
+                return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule stalled for 60 s waiting for block %d (rank %d)", jn, r->rank);
+            std::this_thread::yield();
+        }
+        return RFB_OK;
+    }
+};
+
+// ---- rank set-up / tear-down ---------------------------------------------------------------------------------------------------
+int rank_free_problem(MgRank *r) {
+    if (!r->ctx) return RFB_OK;
+    cudaSetDevice(r->device);
+    cudaDeviceSynchronize();
+    for (void *p : {(void *)r->A, (void *)r->L, (void *)r->stage, (void *)r->ipiv, (void *)r->info, (void *)r->pdst, (void *)r->psrc, (void *)r->pwidth})
+        if (p) cudaFree(p);
+    r->A = r->L = r->stage = nullptr;
+    r->ipiv = r->info = nullptr;
+    r->pdst = r->psrc = r->pwidth = nullptr;
+    for (auto *v : {&r->ev_blk, &r->ev_fact, &r->ev_up}) {
+        for (cudaEvent_t e : *v) if (e) cudaEventDestroy(e);
+        v->clear();
+    }
+    r->ctx->perm_dst = r->ctx->perm_src = r->ctx->perm_width = nullptr;
+    r->ctx->perm_cap = 0;
+    r->ctx->perm_external = false;
+    return RFB_OK;
+}
+
+int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
+    MG_CUDA(r, cudaSetDevice(r->device));
+    rank_free_problem(r);
+    r->plan.build(n, nb, r->world);
+    r->f32 = f32;
+    r->es = f32 ? 4 : 8;
+    const MgPlan &P = r->plan;
+    r->own.clear();
+    r->lcol.assign(P.nblk, -1);
+    r->ncl = 0;
+    for (int j = 0; j < P.nblk; ++j)
+        if (P.owner(j) == r->rank) { r->own.push_back(j); r->lcol[j] = r->ncl; r->ncl += P.width(j); }
+    const size_t nn = (size_t)n;
+    auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
+    bool ok = alloc((void **)&r->L, nn * nn * r->es) && alloc((void **)&r->A, nn * (size_t)std::max<int64_t>(r->ncl, 1) * r->es) &&
+              alloc((void **)&r->stage, nn * (size_t)nb * r->es + 28 * (size_t)nb + 256) && alloc((void **)&r->ipiv, 8 * (nn + 64)) &&
+              alloc((void **)&r->info, 64) && alloc((void **)&r->pdst, 4 * (2 * nn + 128)) && alloc((void **)&r->psrc, 4 * (2 * nn + 128)) &&
+              alloc((void **)&r->pwidth, 4 * (nn + 64));
+    if (!ok) {
+        cudaGetLastError();
+        rank_free_problem(r);
+        return r->fail(RFB_ERR_NOMEM, "rank %d: cannot allocate the replica (%zu bytes) and the own block columns", r->rank, nn * nn * r->es);
+    }
+    r->ctx->perm_dst = r->pdst; r->ctx->perm_src = r->psrc; r->ctx->perm_width = r->pwidth;
+    r->ctx->perm_cap = nn + 64;
+    r->ctx->perm_external = true;
+    r->ev_blk.assign(P.nblk, nullptr);
+    r->ev_fact.assign(P.nblk, nullptr);
+    r->ev_up.assign(P.nblk, nullptr);
+    r->up_pending.assign(P.nblk, 0);
+    for (int j = 0; j < P.nblk; ++j) {
+        MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_blk[j], cudaEventDisableTiming));
+        if (P.owner(j) == r->rank) {
+            MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_fact[j], cudaEventDisableTiming));
+            MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_up[j], cudaEventDisableTiming));
+        }
+    }
+    MG_CUDA(r, cudaMemset(r->info, 0, 64));
+    MG_CUDA(r, cudaDeviceSynchronize());
+    return RFB_OK;
+}
+
+int rank_create(MgRank *r) {
+    rfb_ctx *ctx = nullptr;
+    int rc = rfb_create(&ctx, r->device);
+    r->ctx = ctx;
+    if (rc != RFB_OK) return r->fail(rc, "%s", ctx ? ctx->last_error.c_str() : "rfb_create failed");
+    r->s_comp = ctx->own_stream;
+    int lo = 0, hi = 0;
+    MG_CUDA(r, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MG_CUDA(r, cudaStreamCreateWithPriority(&r->s_L, cudaStreamNonBlocking, hi));
+    MG_CUDA(r, cudaStreamCreateWithFlags(&r->s_copy, cudaStreamNonBlocking));
+    MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_sent, cudaEventDisableTiming));
+    MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_final, cudaEventDisableTiming));
+    MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_chunk[0], cudaEventDisableTiming));
+    MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_chunk[1], cudaEventDisableTiming));
+    MG_CUDA(r, cudaEventCreate(&r->ev_t0));
+    MG_CUDA(r, cudaEventCreate(&r->ev_t1));
+    if (const char *e = getenv("RFB_MG_KMAX")) r->kmax = atoll(e);
+    if (const char *e = getenv("RFB_MG_SLICE_US")) r->slice_us = atof(e);
+    return RFB_OK;
+}
+
+int rank_comm_init(MgRank *r, const ncclUniqueId &id) {
+    NcclApi *api = nccl_api();
+    if (!api->error.empty()) return r->fail(RFB_ERR_NCCL, "%s", api->error.c_str());
+    MG_CUDA(r, cudaSetDevice(r->device));
+    if (api->CommInitRankConfig) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        // the broadcast kernel waits for the owner while GEMM waves run beside it: keep its footprint to a few SMs
+        const char *e = getenv("RFB_MG_NCCL_MAX_CTAS");
+        cfg.maxCTAs = e ? atoi(e) : 8;
+        cfg.minCTAs = 1;
+        MG_NCCL(r, api->CommInitRankConfig(&r->comm, r->world, id, r->rank, &cfg));
+    } else {
+        MG_NCCL(r, api->CommInitRank(&r->comm, r->world, id, r->rank));
+    }
+    return RFB_OK;
+}
+
+void rank_destroy(MgRank *r) {
+    if (!r) return;
+    if (r->ctx) {
+        cudaSetDevice(r->device);
+        rank_free_problem(r);
+        if (r->comm) nccl_api()->CommDestroy(r->comm);
+        for (cudaEvent_t e : {r->ev_sent, r->ev_final, r->ev_chunk[0], r->ev_chunk[1], r->ev_t0, r->ev_t1})
+            if (e) cudaEventDestroy(e);
+        if (r->s_L) cudaStreamDestroy(r->s_L);
+        if (r->s_copy) cudaStreamDestroy(r->s_copy);
+        rfb_destroy(r->ctx);
+    }
+    delete r;
+}
+
+// one factorization on one rank: reset, schedule, close the timer; returns after everything is ENQUEUED
+template <typename T>
+int rank_factor(MgRank *r) {
+    MG_CUDA(r, cudaSetDevice(r->device));
+    const MgPlan &P = r->plan;
+    r->status = RFB_OK;
+    r->ctx->stream = r->s_comp;
+    r->ctx->lane = 0;
+    MG_CUDA(r, cudaEventRecord(r->ev_t0, r->s_comp));
+    MG_CUDA(r, cudaMemsetAsync(r->info, 0, 64, r->s_comp));
+    MG_CUDA(r, cudaMemsetAsync(r->pdst, 0xFF, 4 * (2 * (size_t)P.n + 128), r->s_comp));
+    MG_CUDA(r, cudaMemsetAsync(r->psrc, 0xFF, 4 * (2 * (size_t)P.n + 128), r->s_comp));
+    MG_CUDA(r, cudaMemsetAsync(r->pwidth, 0, 4 * ((size_t)P.n + 64), r->s_comp));
+    // the replica stream must not unpack into the lists before they are cleared
+    MG_CUDA(r, cudaEventRecord(r->ev_sent, r->s_comp));
+    MG_CUDA(r, cudaStreamWaitEvent(r->s_L, r->ev_sent, 0));
+    MgSched<T> sched(r);
+    int rc = sched.run();
+    if (rc != RFB_OK) {
+        if (r->comm && r->world > 1) nccl_api()->CommAbort(r->comm), r->comm = nullptr;     // never leave a collective hanging on the device
+        return rc;
+    }
+    MG_CUDA(r, cudaEventRecord(r->ev_final, r->s_L));
+    MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_final, 0));
+    MG_CUDA(r, cudaEventRecord(r->ev_t1, r->s_comp));
+    return RFB_OK;
+}
+
+int rank_sync(MgRank *r, float *ms) {
+    MG_CUDA(r, cudaSetDevice(r->device));
+    MG_CUDA(r, cudaStreamSynchronize(r->s_comp));
+    MG_CUDA(r, cudaStreamSynchronize(r->s_L));
+    MG_CUDA(r, cudaStreamSynchronize(r->s_copy));
+    unsigned int flag = 0;
+    MG_CUDA(r, cudaMemcpy(&flag, &r->ctx->xchg->error_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(&r->ctx->xchg->error_flag, 0, sizeof(unsigned int));
+        return r->fail(RFB_ERR_INTERNAL, "rank %d: device-side protocol error (flag %u)", r->rank, flag);
+    }
+    if (ms) {
+        *ms = 0;
+        if (cudaEventQuery(r->ev_t1) == cudaSuccess && cudaEventElapsedTime(ms, r->ev_t0, r->ev_t1) != cudaSuccess) { cudaGetLastError(); *ms = 0; }
+    }
+    return RFB_OK;
+}
+
+int mg_fail(rfb_mg *mg, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    mg->last_error = buf;
+    return code;
+}
+
+int collect(rfb_mg *mg) {
+    for (MgRank *r : mg->ranks)
+        if (r->status != RFB_OK) { mg->last_error = r->error; return r->status; }
+    return RFB_OK;
+}
+
+// run fn(rank) on every local rank: inline for one rank, one host thread per device otherwise
+template <typename F>
+int for_ranks(rfb_mg *mg, F fn) {
+    if (mg->ranks.size() == 1) { fn(mg->ranks[0]); return collect(mg); }
+    std::vector<std::thread> th;
+    for (MgRank *r : mg->ranks) th.emplace_back([r, &fn] { fn(r); });
+    for (auto &t : th) t.join();
+    return collect(mg);
+}
+
+MgRank *local(rfb_mg *mg, int lr) { return (mg && lr >= 0 && lr < (int)mg->ranks.size()) ? mg->ranks[lr] : nullptr; }
+
+template <typename T>
+int mg_lu_host(rfb_mg *mg, T *A, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t nb) {
+    if (!mg->all_mode) return mg_fail(mg, RFB_ERR_UNSUPPORTED, "rfb_mg_lu_*: whole-matrix host entry needs a one-process handle (rfb_mg_create_all)");
+    if (n < 0 || lda < std::max<int64_t>(n, 1) || !info) return mg_fail(mg, RFB_ERR_ARG, "bad n / lda / info");
+    if (n == 0) { *info = 0; return RFB_OK; }
+    if (!A || !ipiv) return mg_fail(mg, RFB_ERR_ARG, "A or ipiv is null");
+    if (nb <= 0) nb = 512;
+    if (nb % 64) return mg_fail(mg, RFB_ERR_ARG, "block width must be a multiple of 64");
+    int rc = rfb_mg_setup(mg, n, nb, sizeof(T) == 4);
+    if (rc != RFB_OK) return rc;
+    // upload (each rank its own block columns, in block order: the factorization starts on the first ones), factor, download
+    rc = for_ranks(mg, [&](MgRank *r) {
+        cudaSetDevice(r->device);
+        for (int j : r->own) {
+            const int64_t c0 = r->plan.col0(j), w = r->plan.width(j);
+            if (cudaMemcpy2DAsync(r->Aj(0, r->lcol[j]), n * sizeof(T), A + c0 * lda, lda * sizeof(T), n * sizeof(T), w, cudaMemcpyHostToDevice,
+                                  r->s_copy) != cudaSuccess ||
+                cudaEventRecord(r->ev_up[j], r->s_copy) != cudaSuccess) { r->fail(RFB_ERR_CUDA, "upload of block %d failed", j); return; }
+            r->up_pending[j] = 1;
+        }
+        if (rank_factor<T>(r) != RFB_OK) return;
+        if (cudaStreamWaitEvent(r->s_copy, r->ev_final, 0) != cudaSuccess) { r->fail(RFB_ERR_CUDA, "stream wait failed"); return; }
+        for (int j : r->own) {
+            const int64_t c0 = r->plan.col0(j), w = r->plan.width(j);
+            if (cudaMemcpy2DAsync(A + c0 * lda, lda * sizeof(T), r->Aj(0, r->lcol[j]), n * sizeof(T), n * sizeof(T), w, cudaMemcpyDeviceToHost,
+                                  r->s_copy) != cudaSuccess) { r->fail(RFB_ERR_CUDA, "download of block %d failed", j); return; }
+        }
+        float ms = 0;
+        rank_sync(r, &ms);
+    });
+    if (rc != RFB_OK) return rc;
+    rc = rfb_mg_get_pivots(mg, ipiv);
+    if (rc != RFB_OK) return rc;
+    return rfb_mg_get_info(mg, info);
+}
+
+}  // namespace
+
+// =================================================================================================================================
+extern "C" {
+
+const char *rfb_mg_last_error(rfb_mg *mg) { return mg ? mg->last_error.c_str() : "null handle"; }
+
+int rfb_mg_unique_id(void *id128) {
+    if (!id128) return RFB_ERR_ARG;
+    NcclApi *api = nccl_api();
+    if (!api->error.empty()) return RFB_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return RFB_ERR_NCCL;
+    memcpy(id128, &id, sizeof(id));
+    return RFB_OK;
+}
+
+int rfb_mg_create_rank(rfb_mg **out, int device, int rank, int nranks, const void *id128) {
+    if (!out) return RFB_ERR_ARG;
+    rfb_mg *mg = new rfb_mg();
+    *out = mg;
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) return mg_fail(mg, RFB_ERR_ARG, "bad rank / nranks / id");
+    mg->world = nranks;
+    MgRank *r = new MgRank();
+    r->mg = mg; r->rank = rank; r->world = nranks; r->device = device;
+    mg->ranks.push_back(r);
+    if (rank_create(r) != RFB_OK) return collect(mg);
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        if (rank_comm_init(r, id) != RFB_OK) return collect(mg);
+    }
+    return RFB_OK;
+}
+
+int rfb_mg_create_all(rfb_mg **out, int ngpus, const int *devices) {
+    if (!out) return RFB_ERR_ARG;
+    rfb_mg *mg = new rfb_mg();
+    *out = mg;
+    if (ngpus < 1) return mg_fail(mg, RFB_ERR_ARG, "ngpus must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < ngpus) {
+        cudaGetLastError();
+        return mg_fail(mg, RFB_ERR_CUDA, "%d GPUs requested, %d visible; librfb200 has no CPU fallback", ngpus, ndev);
+    }
+    mg->world = ngpus;
+    mg->all_mode = true;
+    for (int i = 0; i < ngpus; ++i) {
+        MgRank *r = new MgRank();
+        r->mg = mg; r->rank = i; r->world = ngpus; r->device = devices ? devices[i] : i;
+        mg->ranks.push_back(r);
+        if (rank_create(r) != RFB_OK) return collect(mg);
+    }
+    if (ngpus > 1) {
+        NcclApi *api = nccl_api();
+        if (!api->error.empty()) return mg_fail(mg, RFB_ERR_NCCL, "%s", api->error.c_str());
+        ncclUniqueId id;
+        if (api->GetUniqueId(&id) != ncclSuccess) return mg_fail(mg, RFB_ERR_NCCL, "ncclGetUniqueId failed");
+        api->GroupStart();                                    // one process, G devices: all communicators inside one group
+        for (MgRank *r : mg->ranks)
+            if (rank_comm_init(r, id) != RFB_OK) break;
+        if (api->GroupEnd() != ncclSuccess && collect(mg) == RFB_OK) return mg_fail(mg, RFB_ERR_NCCL, "ncclGroupEnd failed");
+        if (collect(mg) != RFB_OK) return collect(mg);
+    }
+    return RFB_OK;
+}
+
+int rfb_mg_destroy(rfb_mg *mg) {
+    if (!mg) return RFB_OK;
+    for (MgRank *r : mg->ranks) rank_destroy(r);
+    delete mg;
+    return RFB_OK;
+}
+
+int rfb_mg_setup(rfb_mg *mg, int64_t n, int64_t nb, int is_f32) {
+    if (!mg) return RFB_ERR_ARG;
+    if (n <= 0 || nb < 64 || nb % 64) return mg_fail(mg, RFB_ERR_ARG, "need n > 0 and a block width that is a positive multiple of 64");
+    if (n > 0x7ffffff0LL) return mg_fail(mg, RFB_ERR_UNSUPPORTED, "dimension exceeds int32");
+    if (mg->n == n && mg->nb == nb && mg->f32 == (is_f32 != 0) && !mg->ranks.empty() && mg->ranks[0]->L) return RFB_OK;   // buffers are reused
+    mg->n = n; mg->nb = nb; mg->f32 = is_f32 != 0;
+    return for_ranks(mg, [&](MgRank *r) { rank_setup(r, n, nb, is_f32 != 0); });
+}
+
+int rfb_mg_local_ranks(rfb_mg *mg, int *count, int *world) {
+    if (!mg) return RFB_ERR_ARG;
+    if (count) *count = (int)mg->ranks.size();
+    if (world) *world = mg->world;
+    return RFB_OK;
+}
+
+int rfb_mg_rank_ctx(rfb_mg *mg, int lr, rfb_ctx **ctx, int *global_rank) {
+    MgRank *r = local(mg, lr);
+    if (!r) return RFB_ERR_ARG;
+    if (ctx) *ctx = r->ctx;
+    if (global_rank) *global_rank = r->rank;
+    return RFB_OK;
+}
+
+int rfb_mg_block_ptr(rfb_mg *mg, int lr, int64_t j, void **dev_ptr) {
+    MgRank *r = local(mg, lr);
+    if (!r || !dev_ptr || !r->A) return RFB_ERR_ARG;
+    if (j < 0 || j >= r->plan.nblk || r->plan.owner((int)j) != r->rank) return mg_fail(mg, RFB_ERR_ARG, "block %lld is not owned by rank %d", (long long)j, r->rank);
+    *dev_ptr = r->Aj(0, r->lcol[j]);
+    return RFB_OK;
+}
+
+// src_kind: 0 host (H2D), 1 device (D2D); the copy runs on the rank's copy stream and the factorization waits for it
+int rfb_mg_load_block(rfb_mg *mg, int lr, int64_t j, const void *src, int64_t ld, int src_kind) {
+    MgRank *r = local(mg, lr);
+    if (!r || !src || !r->A) return RFB_ERR_ARG;
+    if (j < 0 || j >= r->plan.nblk || r->plan.owner((int)j) != r->rank) return mg_fail(mg, RFB_ERR_ARG, "block %lld is not owned by rank %d", (long long)j, r->rank);
+    if (ld < r->plan.n) return mg_fail(mg, RFB_ERR_ARG, "ld < n");
+    cudaSetDevice(r->device);
+    const size_t es = r->es, n = (size_t)r->plan.n;
+    cudaError_t e = cudaMemcpy2DAsync(r->Aj(0, r->lcol[j]), n * es, src, (size_t)ld * es, n * es, (size_t)r->plan.width((int)j),
+                                      src_kind ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, r->s_copy);
+    if (e == cudaSuccess) e = cudaEventRecord(r->ev_up[j], r->s_copy);
+    if (e != cudaSuccess) return mg_fail(mg, RFB_ERR_CUDA, "load of block %lld failed: %s", (long long)j, cudaGetErrorString(e));
+    r->up_pending[j] = 1;
+    return RFB_OK;
+}
+
+int rfb_mg_store_block(rfb_mg *mg, int lr, int64_t j, void *dst_host, int64_t ld) {
+    MgRank *r = local(mg, lr);
+    if (!r || !dst_host || !r->A) return RFB_ERR_ARG;
+    if (j < 0 || j >= r->plan.nblk || r->plan.owner((int)j) != r->rank) return mg_fail(mg, RFB_ERR_ARG, "block %lld is not owned by rank %d", (long long)j, r->rank);
+    cudaSetDevice(r->device);
+    const size_t es = r->es, n = (size_t)r->plan.n;
+    cudaError_t e = cudaStreamWaitEvent(r->s_copy, r->ev_final, 0);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(dst_host, (size_t)ld * es, r->Aj(0, r->lcol[j]), n * es, n * es, (size_t)r->plan.width((int)j), cudaMemcpyDeviceToHost, r->s_copy);
+    if (e != cudaSuccess) return mg_fail(mg, RFB_ERR_CUDA, "store of block %lld failed: %s", (long long)j, cudaGetErrorString(e));
+    return RFB_OK;
+}
+
+int rfb_mg_factor(rfb_mg *mg) {
+    if (!mg || mg->ranks.empty() || !mg->ranks[0]->L) return mg ? mg_fail(mg, RFB_ERR_ARG, "rfb_mg_setup first") : RFB_ERR_ARG;
+    if (mg->f32) return for_ranks(mg, [](MgRank *r) { rank_factor<float>(r); });
+    return for_ranks(mg, [](MgRank *r) { rank_factor<double>(r); });
+}
+
+int rfb_mg_sync(rfb_mg *mg, float *ms) {
+    if (!mg) return RFB_ERR_ARG;
+    float worst = 0;
+    for (MgRank *r : mg->ranks) {
+        float t = 0;
+        if (rank_sync(r, &t) != RFB_OK) return collect(mg);
+        worst = std::max(worst, t);
+    }
+    mg->last_ms = worst;
+    if (ms) *ms = worst;      // max over the LOCAL ranks; one-process-per-GPU callers reduce over processes themselves
+    return RFB_OK;
+}
+
+int rfb_mg_get_pivots(rfb_mg *mg, int64_t *ipiv_host) {
+    MgRank *r = local(mg, 0);
+    if (!r || !ipiv_host || !r->ipiv) return RFB_ERR_ARG;
+    cudaSetDevice(r->device);
+    if (cudaStreamSynchronize(r->s_L) != cudaSuccess || cudaStreamSynchronize(r->s_comp) != cudaSuccess ||
+        cudaMemcpy(ipiv_host, r->ipiv, 8 * (size_t)r->plan.n, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return mg_fail(mg, RFB_ERR_CUDA, "pivot download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return RFB_OK;
+}
+
+// global info: the smallest non-zero per-rank value (first exactly-zero pivot column, src/lu.jl:321-327), else 0
+int rfb_mg_get_info(rfb_mg *mg, int64_t *info) {
+    if (!mg || !info || mg->ranks.empty()) return RFB_ERR_ARG;
+    int64_t best = 0;
+    for (MgRank *r : mg->ranks) {
+        cudaSetDevice(r->device);
+        int64_t v = 0;
+        if (cudaStreamSynchronize(r->s_comp) != cudaSuccess || cudaMemcpy(&v, r->info, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return mg_fail(mg, RFB_ERR_CUDA, "info download failed");
+        if (v != 0 && (best == 0 || v < best)) best = v;
+    }
+    if (!mg->all_mode && mg->world > 1) {                 // one process per GPU: min over the ranks through NCCL
+        MgRank *r = mg->ranks[0];
+        int64_t *d = reinterpret_cast<int64_t *>(r->info) + 1;
+        const int64_t big = INT64_MAX, mine = best == 0 ? big : best;
+        if (cudaMemcpy(d, &mine, 8, cudaMemcpyHostToDevice) != cudaSuccess) return mg_fail(mg, RFB_ERR_CUDA, "info upload failed");
+        if (nccl_api()->AllReduce(d, d, 1, ncclInt64, ncclMin, r->comm, r->s_L) != ncclSuccess) return mg_fail(mg, RFB_ERR_NCCL, "info all-reduce failed");
+        int64_t g = 0;
+        if (cudaStreamSynchronize(r->s_L) != cudaSuccess || cudaMemcpy(&g, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return mg_fail(mg, RFB_ERR_CUDA, "info download failed");
+        best = g == big ? 0 : g;
+    }
+    *info = best;
+    return RFB_OK;
+}
+
+int rfb_mg_stats(rfb_mg *mg, int64_t *bcast_bytes_per_rank, int64_t *launches) {
+    MgRank *r = local(mg, 0);
+    if (!r) return RFB_ERR_ARG;
+    if (bcast_bytes_per_rank) *bcast_bytes_per_rank = r->bcast_bytes;
+    if (launches) { int64_t s = 0; for (MgRank *q : mg->ranks) s += q->ctx->launches; *launches = s; }
+    return RFB_OK;
+}
+
+int rfb_mg_lu_f64(rfb_mg *mg, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block) {
+    if (!mg) return RFB_ERR_ARG;
+    return mg_lu_host<double>(mg, A_host, n, lda, ipiv, info, block);
+}
+int rfb_mg_lu_f32(rfb_mg *mg, float *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block) {
+    if (!mg) return RFB_ERR_ARG;
+    return mg_lu_host<float>(mg, A_host, n, lda, ipiv, info, block);
+}
+
+// convenience: create, factor, destroy (pays the NCCL start-up on every call; keep a handle for repeated use)
+int rfb_lu_f64_mg(const int *devices, int ngpus, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block) {
+    rfb_mg *mg = nullptr;
+    int rc = rfb_mg_create_all(&mg, ngpus, devices);
+    if (rc == RFB_OK) rc = rfb_mg_lu_f64(mg, A_host, n, lda, ipiv, info, block);
+    if (rc != RFB_OK && mg) fprintf(stderr, "rfb_lu_f64_mg: %s\n", mg->last_error.c_str());
+    rfb_mg_destroy(mg);
+    return rc;
+}
+int rfb_lu_f32_mg(const int *devices, int ngpus, float *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block) {
+    rfb_mg *mg = nullptr;
+    int rc = rfb_mg_create_all(&mg, ngpus, devices);
+    if (rc == RFB_OK) rc = rfb_mg_lu_f32(mg, A_host, n, lda, ipiv, info, block);
+    if (rc != RFB_OK && mg) fprintf(stderr, "rfb_lu_f32_mg: %s\n", mg->last_error.c_str());
+    rfb_mg_destroy(mg);
+    return rc;
+}
+
+// Dry run of one rank's schedule (no GPU, no NCCL): 5 int64 per operation, in the order the rank would enqueue them when every
+// input is already there:  [1, c0, n1, j, 0] update of block column j by the node whose left half is columns [c0, c0 + n1)
+// (:233-240);  [2, j, c0, w, 0] factor block column j;  [3, j, root, c0, w] broadcast of block column j;
+// [4, c0, n1, k0, k1] A21 <- P2 A21 (:246): pivots [k0, k1) applied to columns [c0, c0 + n1).
+int rfb_mg_trace(int64_t n, int64_t nb, int rank, int world, int64_t *ops, int64_t cap, int64_t *count) {
+    if (!count || n <= 0 || nb <= 0 || world < 1 || rank < 0 || rank >= world) return RFB_ERR_ARG;
+    MgRank r;
+    r.rank = rank; r.world = world; r.dry = true;
+    std::vector<int64_t> tr;
+    r.trace = &tr;
+    r.plan.build(n, nb, world);
+    r.lcol.assign(r.plan.nblk, -1);
+    for (int j = 0; j < r.plan.nblk; ++j)
+        if (r.plan.owner(j) == rank) { r.own.push_back(j); r.lcol[j] = r.ncl; r.ncl += r.plan.width(j); }
+    MgSched<double> sched(&r);
+    const int rc = sched.run();
+    if (rc != RFB_OK) return rc;
+    *count = (int64_t)tr.size() / 5;
+    if (ops) {
+        const int64_t nout = std::min<int64_t>(*count, cap) * 5;
+        for (int64_t i = 0; i < nout; ++i) ops[i] = tr[(size_t)i];
+    }
+    return RFB_OK;
+}
+
+}  // extern "C"

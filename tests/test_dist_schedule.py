@@ -1,9 +1,9 @@
-"""CPU (gloo, world_size 2 and 3) tests of the multi-GPU schedule.
+"""CPU (gloo, world_size 2, 3 and 4) tests of the multi-GPU schedule.
 
-The product's distributed recursion (`run_schedule` in recursivefactorization.jl_b200/dist_lu.py) is
-host logic over a backend interface; here it is driven by a numpy backend whose kernels are the CPU
-oracle's loops and whose broadcast is torch.distributed/gloo, and the gathered result must equal the
-single-process oracle factorization (pivots exactly, factors to rounding)."""
+The product's distributed recursion is the C++ scheduler of csrc/rfb_mg.cu.  `rfb_mg_trace` runs exactly that code
+dry (no GPU, no NCCL) and returns the operations one rank enqueues; here every rank replays ITS trace with a numpy
+backend whose kernels are the CPU oracle's loops and whose broadcast is torch.distributed/gloo, and the gathered
+result must equal the single-process oracle factorization (pivots exactly, factors to rounding)."""
 import os
 import socket
 import sys
@@ -79,12 +79,26 @@ def _worker(rank, world, port, n, nb, seed, zero_col, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import rfb200
-    from rfb200.dist_lu import run_schedule, owner_of, block_range
+    from rfb200.dist_lu import (TRACE_BCAST, TRACE_FACTOR, TRACE_SWAP_LEFT, TRACE_UPDATE, block_range, owner_of,
+                                trace_schedule)
     a = np.asfortranarray(np.random.default_rng(seed).random((n, n)))
     if zero_col >= 0:
         a[:, zero_col] = 0
     be = NumpyBackend(a, nb, rank, world)
-    run_schedule(be, n, nb, rank, world)
+    for code, x0, x1, x2, x3 in trace_schedule(n, nb, rank, world).tolist():
+        if code == TRACE_UPDATE:                      # [1, c0, n1, j, 0]
+            assert owner_of(x2, world) == rank
+            be.update([x2], x0, x1)
+        elif code == TRACE_FACTOR:                    # [2, j, c0, w, 0]
+            assert owner_of(x0, world) == rank and (x1, x2) == block_range(x0, n, nb)
+            be.factor_block(x1, x2)
+        elif code == TRACE_BCAST:                     # [3, j, root, c0, w]
+            assert x1 == owner_of(x0, world)
+            be.bcast_block(x2, x3, x1)
+        elif code == TRACE_SWAP_LEFT:                 # [4, c0, n1, k0, k1]
+            be.swap_left(x0, x1, x2, x3)
+        else:
+            raise AssertionError(code)
     # gather: every rank contributes its own block columns
     full = torch.zeros((n, n), dtype=torch.float64)
     for j in range((n + nb - 1) // nb):
@@ -108,7 +122,8 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,n,nb,zero_col", [(2, 256, 64, -1), (2, 300, 64, -1), (3, 448, 64, -1), (2, 256, 64, 100)])
+@pytest.mark.parametrize("world,n,nb,zero_col", [(2, 256, 64, -1), (2, 300, 64, -1), (3, 448, 64, -1), (2, 256, 64, 100),
+                                                 (4, 704, 64, -1)])
 def test_block_cyclic_schedule_matches_oracle(tmp_path, world, n, nb, zero_col):
     sys.path.insert(0, ROOT)
     from oracle import rf_oracle as O
@@ -134,3 +149,32 @@ def test_ownership_helpers():
     assert owned_blocks(1, 4, 1000, 128) == [1, 5]
     assert block_range(7, 1000, 128) == (896, 104)
     assert sum(block_range(j, 1000, 128)[1] for j in range(8)) == 1000
+
+
+def test_trace_is_left_looking_per_block_and_complete():
+    """Structure of the C++ schedule: every block column is broadcast exactly once and in block order on every rank,
+    an owned block column receives one update per ancestor whose right half holds it (top-down, the lowest last),
+    then is factored, then published; A21 <- P2 A21 (src/lu.jl:246) appears once per internal node on every rank."""
+    sys.path.insert(0, ROOT)
+    import rfb200  # noqa: F401
+    from rfb200.dist_lu import TRACE_BCAST, TRACE_FACTOR, TRACE_SWAP_LEFT, TRACE_UPDATE, trace_schedule
+    n, nb, world = 64 * 13, 64, 4
+    nblk = 13
+    swaps = None
+    for rank in range(world):
+        t = trace_schedule(n, nb, rank, world).tolist()
+        assert [op[1] for op in t if op[0] == TRACE_BCAST] == list(range(nblk))
+        mine = [j for j in range(nblk) if j % world == rank]
+        assert [op[1] for op in t if op[0] == TRACE_FACTOR] == mine
+        for j in mine:
+            ups = [(op[1], op[2]) for op in t if op[0] == TRACE_UPDATE and op[3] == j]
+            assert all(c0 + n1 <= j * nb for c0, n1 in ups)                       # the left half ends before block j
+            assert [u[1] for u in ups] == sorted((u[1] for u in ups), reverse=True)   # top-down: widest left half first
+            if j > 0:
+                assert ups and ups[-1][0] + ups[-1][1] == j * nb                   # the lowest update: left half ends right before j
+            i_f = t.index([TRACE_FACTOR, j, j * nb, min(nb, n - j * nb), 0])
+            assert all(t.index(op) < i_f for op in t if op[0] == TRACE_UPDATE and op[3] == j)
+        sw = [tuple(op[1:]) for op in t if op[0] == TRACE_SWAP_LEFT]
+        assert len(sw) == nblk - 1                                                 # one per internal node of the block tree
+        swaps = swaps or sw
+        assert sw == swaps                                                         # same on every rank, same order

@@ -52,7 +52,7 @@ def hutchinson_residual(a0, factors, ipiv, nvec=8, seed=0):
     ux = np.triu(f[:mn, :]) @ x
     lux = np.tril(f[:, :mn], -1) @ ux
     lux[:mn] += ux
-    pax = np.asarray(a0, dtype=np.float64)[p, :] @ x
+    pax = (np.asarray(a0, dtype=np.float64) @ x)[p]
     num = np.linalg.norm(pax - lux) / np.sqrt(nvec)
     return float(num / np.linalg.norm(np.asarray(a0, dtype=np.float64)))
 
