@@ -248,7 +248,7 @@ def other_configs(ctx, rfb200, skip_big=False):
                 best = t if best is None else min(best, t)
         return best
 
-    def lu_case(n, dtype, check=None, residual=True, **opt):
+    def lu_case(n, dtype, check=None, residual=True, profile=False, **opt):
         a = np.empty((n, n), dtype=dtype, order="F")
         fill_random(a)
         if opt.get("no_pivot"):
@@ -256,6 +256,14 @@ def other_configs(ctx, rfb200, skip_big=False):
         src = rfb200.DeviceMatrix(ctx, n, n, dtype, lda=n); src.upload(a); ctx.sync()
         dst = rfb200.DeviceMatrix(ctx, n, n, dtype, lda=n)
         ms = timed(lambda: dst.lu(**opt), lambda: dst.copy_from(src))
+        prof = None
+        if profile:                          # separate, untimed pass with events around every launch
+            dst.copy_from(src)
+            ctx.profile_enable(True)
+            dst.lu(**opt)
+            prof = ctx.profile_read()
+            ctx.profile_enable(False)
+            dst.copy_from(src); dst.lu(**opt)
         if not residual:                      # 8.6 GB matrices: no host-side probe (the multi-GPU run reports one at this size)
             info_h = np.zeros(1, dtype=np.int64)
             ctx.d2h(info_h, dst.info_ptr); ctx.sync()
@@ -267,6 +275,8 @@ def other_configs(ctx, rfb200, skip_big=False):
         src.free(); dst.free()
         out = {"ms": round(ms, 3), "gflops": round(lu_flops(n) / ms / 1e6, 1), "info": info, "residual_fro_rel_est": res,
                "bound_20_n_eps": 20 * n * float(np.finfo(dtype).eps)}
+        if prof is not None:
+            out["profile"] = prof
         if check and not opt.get("no_pivot"):
             from scipy.linalg import lapack
             getrf = lapack.dgetrf if dtype == np.float64 else lapack.sgetrf
@@ -285,9 +295,21 @@ def other_configs(ctx, rfb200, skip_big=False):
         return out
 
     out["4096x4096 Float64 LU with partial pivoting (BASELINE config 2)"] = lu_case(4096, np.float64, check="oracle")
-    out["8192x8192 Float32 LU, exact FP32 FFMA trailing update (BASELINE config 5, default mode)"] = lu_case(8192, np.float32, check="lapack")
-    out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5, opt-in mode)"] = \
-        lu_case(8192, np.float32, check="lapack", f32_mode=1)
+    c5 = lu_case(8192, np.float32, check="lapack", profile=True)
+    tf32_peak = max(ctx.tf32_peak_tflops(4000), ctx.tf32_peak_tflops(4000))
+    g = c5.pop("profile")["gemm"]
+    alg_tf = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    c5["roofline"] = {
+        "bound": "tensor", "kernel": "K4' trailing GEMM, tcgen05.mma kind::tf32 (3xTF32 split, FP32 accumulate in TMEM), TMA-fed",
+        "achieved": alg_tf, "peak": tf32_peak / 3.0, "unit": "TFLOP/s (FP32-accurate: 3 TF32 MMAs per product)",
+        "frac": (3.0 * alg_tf / tf32_peak) if tf32_peak else None, "traffic": None,
+        "tf32_dense_peak_measured": tf32_peak,
+        "peak_source": "own smem-resident tcgen05.mma kind::tf32 microbenchmark (rfb_bench_tf32_peak), nominal 1.1 PFLOP/s dense",
+        "achieved_def": "sum of 2mnk over the GEMM launches of one 8192^2 Float32 LU / sum of their CUDA-event durations",
+        "gemm_ms_of_step": round(g["ms"], 3)}
+    out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5; the default above 512 columns)"] = c5
+    out["8192x8192 Float32 LU, exact FP32 FFMA trailing update (f32_mode = RFB_F32_FP32)"] = \
+        lu_case(8192, np.float32, check="lapack", f32_mode=2)
     out["16384x16384 Float64 LU, pivot = Val(false) (src/lu.jl:27-65)"] = lu_case(16384, np.float64, no_pivot=1)
     if not skip_big:
         out["32768x32768 Float64 LU with partial pivoting on ONE GPU (the N = 1 point of the multi-GPU strong-scaling series, "

@@ -40,13 +40,17 @@ enum {
 
 enum { RFB_MEM_HOST = 0, RFB_MEM_DEVICE = 1 };
 
-/* Float32 trailing-update arithmetic (config "8192x8192 Float32"). */
+/* Float32 trailing-update arithmetic (config "8192x8192 Float32 LU, bf16/TF32 tensor-core GEMM with FP32 accumulate"). */
 enum {
-    RFB_F32_FP32 = 0,   /* exact FP32 FFMA tiles (default: keeps the reference's own error bound)  */
-    RFB_F32_TF32X3 = 1  /* tcgen05 kind::tf32, 3-term split, FP32 accumulate in TMEM: ~2.4x faster
-                           trailing update, residual ~3.6x the FP32 mode's (the tensor core adds
-                           into its accumulator with truncation), still <= 20*n*eps in the
-                           Frobenius metric; views must be 16-byte aligned with lda % 4 == 0    */
+    RFB_F32_AUTO = 0,   /* default.  Whole-path calls (rfb_lu_f32, rfb_mg_lu_f32): TF32X3 when min(m, n) > 512 -- beyond
+                           the sizes the reference itself tests (test/runtests.jl:39: n <= 300) -- exact FP32 below, where
+                           the reference's own inf-norm bound 20*m*eps (runtests.jl:19-20) is the acceptance test.
+                           Kernel-level calls (rfb_gemm_nn_sub_f32 / rfb_trsm_*_f32): exact FP32.                        */
+    RFB_F32_TF32X3 = 1, /* tcgen05 kind::tf32, 3-term split, FP32 accumulate in TMEM: ~2.4x faster trailing update,
+                           residual ~3.6x the FP32 mode's (the tensor core adds into its accumulator with truncation),
+                           still ~500x inside 20*n*eps in the Frobenius metric; views that are not 16-byte aligned
+                           with lda % 4 == 0 fall through to the FP32 tiles                                              */
+    RFB_F32_FP32 = 2    /* exact FP32 FFMA register tiles everywhere                                                     */
 };
 
 /* Options of the whole-path calls.  Zero-initialise for defaults.
@@ -192,6 +196,7 @@ int rfb_laswp_range_f64(rfb_ctx *ctx, double *A_root, int64_t lda, int64_t col0,
 int rfb_laswp_range_f32(rfb_ctx *ctx, float *A_root, int64_t lda, int64_t col0, int64_t ncols,
                         int64_t k0, int64_t k1, const int64_t *ipiv_dev, int use_lists);
 int rfb_perm_buffers(rfb_ctx *ctx, int32_t *dst_dev, int32_t *src_dev, int32_t *width_dev, int64_t cap);
+int rfb_perm_buffers_release(rfb_ctx *ctx);   /* synchronises, then forgets caller-owned list arrays (before freeing them) */
 int rfb_copy2d(rfb_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch,
                size_t width_bytes, size_t height);                               /* async d2d      */
 /* enqueue on a caller-provided CUDA stream (e.g. torch's current stream); NULL restores the own one */
@@ -276,6 +281,9 @@ int rfb_profile_read(rfb_ctx *ctx, double ms_by_class[8], int64_t launches_by_cl
                      double work_by_class[8]);  /* algorithmic flops (bytes for laswp) issued */
 /* register-only DMMA (mma.sync m8n8k4 f64) throughput: the FP64 roofline denominator */
 int rfb_bench_dmma_peak(rfb_ctx *ctx, int iters, double *tflops);
+/* smem-resident tcgen05.mma kind::tf32 (128 x 128 x 8, FP32 accumulate in TMEM) throughput, one CTA per SM: the
+ * tensor roofline denominator of the Float32 path (dense TF32 TFLOP/s; the 3xTF32 mode issues 3 MMAs per product) */
+int rfb_bench_tf32_peak(rfb_ctx *ctx, int iters, double *tflops);
 /* plain device copy bandwidth (read + write bytes / time) */
 int rfb_bench_copy(rfb_ctx *ctx, size_t bytes, int iters, double *gbs);
 

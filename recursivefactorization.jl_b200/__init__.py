@@ -272,6 +272,11 @@ class Context:
         self._check(self._lib.rfb_bench_dmma_peak(self._h, iters, C.byref(v)))
         return float(v.value)
 
+    def tf32_peak_tflops(self, iters: int = 4000) -> float:
+        v = C.c_double()
+        self._check(self._lib.rfb_bench_tf32_peak(self._h, iters, C.byref(v)))
+        return float(v.value)
+
     def copy_gbs(self, nbytes: int = 1 << 30, iters: int = 5) -> float:
         v = C.c_double()
         self._check(self._lib.rfb_bench_copy(self._h, nbytes, iters, C.byref(v)))

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "librfb200.so")
 
 RFB_OK, RFB_ERR_ARG, RFB_ERR_CUDA, RFB_ERR_NCCL, RFB_ERR_UNSUPPORTED, RFB_ERR_NOMEM, RFB_ERR_INTERNAL = range(7)
 RFB_MEM_HOST, RFB_MEM_DEVICE = 0, 1
-RFB_F32_FP32, RFB_F32_TF32X3 = 0, 1
+RFB_F32_AUTO, RFB_F32_TF32X3, RFB_F32_FP32 = 0, 1, 2
 
 STATUS_NAMES = {
     RFB_OK: "RFB_OK", RFB_ERR_ARG: "RFB_ERR_ARG", RFB_ERR_CUDA: "RFB_ERR_CUDA", RFB_ERR_NCCL: "RFB_ERR_NCCL",
@@ -76,6 +76,7 @@ SIGNATURES = {
     "rfb_laswp_range_f64": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),
     "rfb_laswp_range_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _int]),
     "rfb_perm_buffers": (_int, [_p, _p, _p, _p, _i64]),
+    "rfb_perm_buffers_release": (_int, [_p]),
     "rfb_copy2d": (_int, [_p, _p, C.c_size_t, _p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "rfb_set_stream": (_int, [_p, _p]),
     "rfb_mg_unique_id": (_int, [_p]),
@@ -115,6 +116,7 @@ SIGNATURES = {
     "rfb_profile_read": (_int, [_p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)]),
     "rfb_bench_dmma_peak": (_int, [_p, _int, C.POINTER(C.c_double)]),
     "rfb_bench_copy": (_int, [_p, C.c_size_t, _int, C.POINTER(C.c_double)]),
+    "rfb_bench_tf32_peak": (_int, [_p, _int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -231,6 +231,46 @@ gemm_f32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
 }
 
+// Tensor-pipe peak: every CTA issues `iters` back-to-back 128 x 128 x 8 kind::tf32 MMAs on operands that sit in shared
+// memory (same descriptors / layouts as the GEMM above), accumulating in TMEM; nothing is loaded, nothing is stored.
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, float *sink) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned long long *done = reinterpret_cast<unsigned long long *>(base + 2 * kTileBytes);
+    unsigned int *tmem_slot = reinterpret_cast<unsigned int *>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *f = reinterpret_cast<float *>(base);
+    for (int i = tid; i < 2 * kTileBytes / 4; i += 128) f[i] = 1.0f + (float)(i & 7) * 0.125f;
+    if (tid == 0) {
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned int tmem = *tmem_slot;
+    if (warp == 0 && lane == 0) {
+        const unsigned int a = smem_u32(base), b = a + kTileBytes;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                umma_tf32(tmem, make_desc(a + ks * 1024, 4096, 512, 1), make_desc(b + ks * 32, 16, 1024, 2), (it | ks) != 0);
+        }
+        umma_commit(done);
+    }
+    mbar_wait(done, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (sink && tid == 0 && iters < 0) sink[blockIdx.x] = 0.f;      // (keeps `sink` alive; never taken)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -266,5 +306,34 @@ int rfb_launch_gemm_f32_tc(rfb_ctx *ctx, float *C, const float *A, const float *
         mapA, mapB, C, (int)m, (int)n, (int)k, lda, tiles_m, tiles_n);
     RFB_CUDA(ctx, cudaGetLastError());
     *handled = true;
+    return RFB_OK;
+}
+
+int rfb_run_tf32_peak(rfb_ctx *ctx, int iters, double *tflops) {
+    if (iters <= 0) iters = 4000;
+    constexpr size_t smem = 2 * kTileBytes + 1024 + 64;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)tf32_peak_kernel, smem));
+    cudaEvent_t e0, e1;
+    RFB_CUDA(ctx, cudaEventCreate(&e0));
+    RFB_CUDA(ctx, cudaEventCreate(&e1));
+    const int blocks = ctx->sm_count;
+    tf32_peak_kernel<<<blocks, 128, smem, ctx->stream>>>(iters / 10 + 1, nullptr);      // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        RFB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        tf32_peak_kernel<<<blocks, 128, smem, ctx->stream>>>(iters, nullptr);
+        RFB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        RFB_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        RFB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)blocks * (double)iters * 4.0 * 2.0 * CBM * CBN * 8.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    RFB_CUDA(ctx, cudaGetLastError());
+    *tflops = best;
     return RFB_OK;
 }

@@ -124,6 +124,11 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
               const rfb_opts *opts, std::vector<cudaEvent_t> *up_events = nullptr, const std::vector<int64_t> *up_bounds = nullptr,
               T *host_A = nullptr, int64_t host_lda = 0, int64_t *early_rows = nullptr) {
     LuPlan plan;
+    // Float32 arithmetic of the trailing update: resolve RFB_F32_AUTO once per factorization (include/rfb200.h)
+    rfb_opts resolved = opts ? *opts : rfb_opts{};
+    if (sizeof(T) == 4 && resolved.f32_mode == RFB_F32_AUTO)
+        resolved.f32_mode = (m < n ? m : n) > 512 ? RFB_F32_TF32X3 : RFB_F32_FP32;
+    opts = &resolved;
     plan.opts = opts;
     plan.up_events = up_events;
     plan.up_bounds = up_bounds;
@@ -748,6 +753,16 @@ int rfb_perm_buffers(rfb_ctx *ctx, int32_t *dst_dev, int32_t *src_dev, int32_t *
     RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_width, 0, (size_t)cap * sizeof(int), ctx->stream));
     return RFB_OK;
 }
+int rfb_perm_buffers_release(rfb_ctx *ctx) {
+    if (!ctx) return RFB_ERR_ARG;
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->perm_external) {
+        ctx->perm_dst = ctx->perm_src = ctx->perm_width = nullptr;
+        ctx->perm_cap = 0;
+        ctx->perm_external = false;
+    }
+    return RFB_OK;
+}
 int rfb_copy2d(rfb_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch, size_t width_bytes,
                size_t height) {
     if (!ctx) return RFB_ERR_ARG;
@@ -987,6 +1002,11 @@ int rfb_bench_dmma_peak(rfb_ctx *ctx, int iters, double *tflops) {
     RFB_CHECK_CTX(ctx);
     if (!tflops) return ctx->fail(RFB_ERR_ARG, "tflops is null");
     return rfb_run_dmma_peak(ctx, iters, tflops);
+}
+int rfb_bench_tf32_peak(rfb_ctx *ctx, int iters, double *tflops) {
+    RFB_CHECK_CTX(ctx);
+    if (!tflops) return ctx->fail(RFB_ERR_ARG, "tflops is null");
+    return rfb_run_tf32_peak(ctx, iters, tflops);
 }
 int rfb_bench_copy(rfb_ctx *ctx, size_t bytes, int iters, double *gbs) {
     RFB_CHECK_CTX(ctx);

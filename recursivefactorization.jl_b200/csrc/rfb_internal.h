@@ -218,6 +218,7 @@ template <typename T>
 int rfb_launch_gemm_skinny(rfb_ctx *ctx, T *C, const T *A, const T *B, int64_t m, int64_t n, int64_t k, int64_t lda);
 int rfb_launch_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift);
 int rfb_run_dmma_peak(rfb_ctx *ctx, int iters, double *tflops);
+int rfb_run_tf32_peak(rfb_ctx *ctx, int iters, double *tflops);
 int rfb_run_copy_bench(rfb_ctx *ctx, size_t bytes, int iters, double *gbs);
 
 // src/lu.jl:158-162

@@ -154,8 +154,159 @@ trsm_block_kernel(const T *__restrict__ L, int kb, T *__restrict__ B, long long 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Float64 block solve, round 2: warp-independent, DMMA-fed (trsm_dmma_kernel).
+//
+// The kernel above spends a 256-row block in ~50 us whatever the number of right-hand sides: ten 64 x 64 sub-block
+// steps, each with block-wide barriers, 512 dependent shared-memory broadcasts per thread and the FP64 pipe 21 % busy
+// (profiles/r01_trsm_block_kernel.txt) -- and a 16384^2 LU runs 384 such launches back to back.  Here
+//   * every WARP owns 8 right-hand-side columns and walks the whole triangle on its own: no barrier inside a
+//     sub-block step, only one per staged 64 x 64 tile of L (ten per 256 rows);
+//   * the unknowns live in registers in the DMMA accumulator layout (8 m-tiles x 2 doubles); an off-diagonal sub-block
+//     x_s -= L_st x_t is 128 mma.sync.m8n8k4.f64 per warp, with L fragments read conflict-free from a padded shared
+//     tile and x_t fragments from the warp's own staging slot (stored negated, so the MMA accumulates the subtraction);
+//   * a diagonal 64 x 64 triangle goes in eight 8-row micro-blocks: forward substitution inside the micro-block with
+//     warp shuffles (the dependent chain: 7 steps of shuffle + FMA), then the rows below take the micro-block's
+//     contribution as two DMMAs per m-tile;
+//   * L tiles are prefetched one ahead with cp.async into a double buffer shared by the CTA's warps.
+// Substitution order per unknown is still "all earlier unknowns, in order"; only the association inside the 4-term
+// DMMA dot products differs from the FMA chain, so results agree with the oracle to rounding, not bit for bit.
+constexpr int kLdTile = 72;      // padded column stride (doubles): fragment reads of 4 columns x 8 rows hit all 32 banks twice
+
+__device__ __forceinline__ void trsm_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void trsm_cp_async8(double *dst, const double *src, int src_bytes) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32)
+trsm_dmma_kernel(const double *__restrict__ L, int kb, double *__restrict__ B, long long nrhs, long long lda) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sL = reinterpret_cast<double *>(smem_raw);               // [2][64 cols][kLdTile]
+    double *sXall = sL + 2 * 64 * kLdTile;                           // [W][4 sub-blocks][64 rows][8 cols], NEGATED unknowns
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double *sx = sXall + warp * (4 * 64 * 8);
+    const long long col0 = (long long)blockIdx.x * (W * 8) + warp * 8;
+    const int nsub = (kb + 63) >> 6;
+    const int ntiles = nsub * (nsub + 1) / 2;
+
+    auto load_tile = [&](int s, int t, int buf) {
+        double *dstb = sL + buf * 64 * kLdTile;
+        for (int e = tid; e < 64 * 64; e += W * 32) {
+            const int r = e & 63, c = e >> 6;
+            const int gr = s * 64 + r, gc = t * 64 + c;
+            const bool ok = gr < kb && gc < kb;
+            trsm_cp_async8(dstb + c * kLdTile + r, L + (ok ? (long long)gr + (long long)gc * lda : 0), ok ? 8 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    load_tile(0, 0, 0);
+    int idx = 0;
+    for (int s = 0; s < nsub; ++s) {
+        double xc[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = s * 64 + 8 * i + g;
+                const long long col = col0 + 2 * q + e;
+                xc[i][e] = (row < kb && col < nrhs) ? B[row + col * lda] : 0.0;
+            }
+        for (int t = 0; t <= s; ++t, ++idx) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                   // tile idx has landed; every warp is done with tile idx - 1
+            if (idx + 1 < ntiles) {
+                const int s2 = (t == s) ? s + 1 : s, t2 = (t == s) ? 0 : t + 1;
+                load_tile(s2, t2, (idx + 1) & 1);
+            }
+            const double *tL = sL + (idx & 1) * 64 * kLdTile;
+            if (t < s) {                                       // x_s -= L_st x_t
+                const double *xt = sx + t * (64 * 8);
+#pragma unroll 4
+                for (int kk = 0; kk < 16; ++kk) {
+                    const double b = xt[(4 * kk + q) * 8 + g];
+                    const double *ta = tL + (4 * kk + q) * kLdTile + g;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) trsm_dmma(xc[i][0], xc[i][1], ta[8 * i], b);
+                }
+            } else {                                           // the 64 x 64 unit-lower triangle
+                double *xs = sx + s * (64 * 8);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    // rows 8p .. 8p+7: this lane's row is 8p + g; it needs L[8p+g][8p+r] for r < g
+                    double lrow[7];
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) lrow[r] = tL[(8 * p + r) * kLdTile + 8 * p + g];
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        const double x0 = __shfl_sync(0xffffffffu, xc[p][0], (r << 2) | q);
+                        const double x1 = __shfl_sync(0xffffffffu, xc[p][1], (r << 2) | q);
+                        if (g > r) {
+                            xc[p][0] = fma(-lrow[r], x0, xc[p][0]);
+                            xc[p][1] = fma(-lrow[r], x1, xc[p][1]);
+                        }
+                    }
+                    // publish -x_p in the B-fragment layout, then the rows below take its contribution
+                    *reinterpret_cast<double2 *>(xs + (8 * p + g) * 8 + 2 * q) = make_double2(-xc[p][0], -xc[p][1]);
+                    __syncwarp();
+                    if (p < 7) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const double b = xs[(8 * p + 4 * kk + q) * 8 + g];
+                            const double *ta = tL + (8 * p + 4 * kk + q) * kLdTile + g;
+#pragma unroll
+                            for (int i = p + 1; i < 8; ++i) trsm_dmma(xc[i][0], xc[i][1], ta[8 * i], b);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int row = s * 64 + 8 * i + g;
+                        const long long col = col0 + 2 * q + e;
+                        if (row < kb && col < nrhs) B[row + col * lda] = xc[i][e];
+                    }
+            }
+        }
+    }
+}
+
+template <int W>
+int launch_dmma(rfb_ctx *ctx, const double *L, int kb, double *B, int64_t nrhs, int64_t lda) {
+    constexpr size_t smem = sizeof(double) * (2 * 64 * kLdTile + (size_t)W * 4 * 64 * 8);
+    auto kern = trsm_dmma_kernel<W>;
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
+    RfbLaunchScope scope(ctx, RFB_KC_TRSM, (double)kb * (double)kb * (double)nrhs);
+    kern<<<(unsigned int)((nrhs + W * 8 - 1) / (W * 8)), W * 32, smem, ctx->stream>>>(L, kb, B, nrhs, lda);
+    RFB_CUDA(ctx, cudaGetLastError());
+    return RFB_OK;
+}
+
 template <typename T>
-int launch_block(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
+int launch_block_legacy(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda);
+
+template <typename T>
+int launch_block(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda, bool legacy) {
+    if constexpr (sizeof(T) == 8) {
+        if (!legacy) {
+            // 8 warps x 8 columns per CTA once that still gives every SM a CTA; 4 warps otherwise (more CTAs in flight)
+            if (nrhs >= (int64_t)ctx->sm_count * 48) return launch_dmma<8>(ctx, L, kb, B, nrhs, lda);
+            return launch_dmma<4>(ctx, L, kb, B, nrhs, lda);
+        }
+    }
+    return launch_block_legacy<T>(ctx, L, kb, B, nrhs, lda);
+}
+
+template <typename T>
+int launch_block_legacy(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {
     constexpr size_t smem = sizeof(T) * (kSub * kSub + 4 * kSub * kBlkCols);
     auto kern = trsm_block_kernel<T>;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
@@ -296,7 +447,7 @@ int trsm_rec(rfb_ctx *ctx, const T *L, int64_t k, T *B, int64_t nrhs, int64_t ld
     if (k <= tb) {
         if (tb == 32) return launch_diag<T, 32>(ctx, L, (int)k, B, nrhs, lda);
         if (tb == 64) return launch_diag<T, 64>(ctx, L, (int)k, B, nrhs, lda);
-        return launch_block<T>(ctx, L, (int)k, B, nrhs, lda);
+        return launch_block<T>(ctx, L, (int)k, B, nrhs, lda, opts && opts->trsm_block == 1);
     }
     // split at a multiple of the diagonal block nearest to k/2
     int64_t k1 = ((k / 2 + tb - 1) / tb) * tb;

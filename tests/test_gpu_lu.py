@@ -171,13 +171,13 @@ def test_baseline_config_16384_properties(ctx):
 
 @pytest.mark.parametrize("n", [300, 512, 2048, 4096])
 def test_f32_tensor_core_mode(ctx, n):
-    """Float32 LU with the trailing update on tcgen05 (opt-in f32_mode = TF32X3).  Stated tolerance:
+    """Float32 LU with the trailing update on tcgen05 (f32_mode = TF32X3; the default above 512 columns).  Stated tolerance:
     the north_star bound ||PA-LU||_F/||A||_F <= 20*n*eps(Float32) (met with a ~500x margin), a residual
     within 6x of the exact-FP32 mode's (the tensor core accumulates with truncation), and -- inside the
     reference's own tested range n <= 300 -- the reference's inf-norm bound 20*n*eps as well."""
     a0 = np.asfortranarray(np.random.default_rng([12, n]).random((n, n), dtype=np.float32))
     F1 = rfb200.lu(a0, ctx=ctx, f32_mode=1)
-    F0 = rfb200.lu(a0, ctx=ctx, f32_mode=0)
+    F0 = rfb200.lu(a0, ctx=ctx, f32_mode=2)
     assert F1.info == 0
     assert sorted(O.perm_from_ipiv(F1.ipiv, n).tolist()) == list(range(n))
     eps = float(np.finfo(np.float32).eps)
@@ -286,3 +286,25 @@ def test_node_level_laswp_paths_agree(ctx, dtype, shape, monkeypatch):
         assert np.array_equal(F0.ipiv, want_p)
     else:
         assert_pivots_match(a0, F0.factors, F0.ipiv, want_p, strict=False)
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (1000, 1000)), (np.float64, (777, 1300)), (np.float64, (1500, 640)),
+                                         (np.float32, (900, 900)), (np.float64, (130, 130))])
+def test_host_driven_recursion_over_kernel_abi_matches_library_driver(ctx, dtype, shape):
+    """north_star: "Julia host code drives the recursion and calls the kernels through a thin ccall shim".  The shim's
+    `lu_device!` / `reckernel_device!` (julia/RecursiveFactorizationB200.jl, un-executable here) has an executable twin,
+    rfb200.host_recursion.lu_device_, issuing the identical kernel-level calls through ctypes: square, fat (src/lu.jl:148-154)
+    and tall shapes, both element types.  Same kernels in the same order as the C++ driver => bit-identical results."""
+    from rfb200.host_recursion import lu_device_
+    m, n = shape
+    a0 = rand_matrix(np.random.default_rng([55, m, n]), m, n, dtype)
+    d = rfb200.DeviceMatrix(ctx, m, n, dtype, lda=m + (m & 1))
+    d.upload(a0)
+    ctx.sync()
+    lu_device_(ctx, d.ptr, m, n, d.lda, d.ipiv_ptr, d.info_ptr, dtype)
+    f, ipiv, info = d.download()
+    d.free()
+    F = rfb200.lu(a0, check=False, ctx=ctx, f32_mode=2)      # kernel-level GEMM calls are exact FP32 (RFB_F32_AUTO there)
+    assert info == F.info == 0
+    assert np.array_equal(ipiv, F.ipiv)
+    assert np.array_equal(f, F.factors)
