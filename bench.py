@@ -307,7 +307,7 @@ def other_configs(ctx, rfb200, skip_big=False):
         "peak_source": "own smem-resident tcgen05.mma kind::tf32 microbenchmark (rfb_bench_tf32_peak), nominal 1.1 PFLOP/s dense",
         "achieved_def": "sum of 2mnk over the GEMM launches of one 8192^2 Float32 LU / sum of their CUDA-event durations",
         "gemm_ms_of_step": round(g["ms"], 3)}
-    out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5; the default above 512 columns)"] = c5
+    out["8192x8192 Float32 LU, tcgen05 kind::tf32 3xTF32 trailing update (BASELINE config 5; the default from 4096 columns up)"] = c5
     out["8192x8192 Float32 LU, exact FP32 FFMA trailing update (f32_mode = RFB_F32_FP32)"] = \
         lu_case(8192, np.float32, check="lapack", f32_mode=2)
     out["16384x16384 Float64 LU, pivot = Val(false) (src/lu.jl:27-65)"] = lu_case(16384, np.float64, no_pivot=1)

@@ -101,7 +101,8 @@ constexpr int kNetMaxRows = 45056;       // rows the composition can track in sh
 // meta[0] cursor (next pivot to compose), meta[1] chunk k0, meta[2] chunk n1, meta[3] nC (scatter entries)
 __global__ void __launch_bounds__(kComposeThreads)
 laswp_compose_kernel(const int *__restrict__ perm_dst, const int *__restrict__ perm_src, const int *__restrict__ perm_width,
-                     int k0, int k1, int row_bound, int cap, int first_round, int *__restrict__ meta, int *__restrict__ srcmap,
+                     int k0, int k1, int row_bound, int cap, int first_round, int stage_lists, int *__restrict__ meta,
+                     int *__restrict__ srcmap,
                      int *__restrict__ clist, unsigned int *__restrict__ error_flag) {
     extern __shared__ int cur[];                         // cur[r - start] = original row whose content is now at row r
     __shared__ int pstart[kMaxPanelsPerChunk + 1];
@@ -145,6 +146,31 @@ laswp_compose_kernel(const int *__restrict__ perm_dst, const int *__restrict__ p
     }
     const int R = row_bound - start;
     for (int r = tid; r < R; r += kComposeThreads) cur[r] = start + r;
+    const int n1 = end - start;
+    if (stage_lists) {
+        // the chunk's lists fit beside `cur`: stage them with all threads (coalesced), then ONE group of 128 threads walks the
+        // panels out of shared memory with a 4-warp named barrier -- ~100 cycles per panel instead of two 32-warp barriers
+        int *sdst = cur + R, *ssrc = sdst + 2 * n1;
+        for (int i = tid; i < 2 * n1; i += kComposeThreads) {
+            sdst[i] = perm_dst[2 * start + i];
+            ssrc[i] = perm_src[2 * start + i];
+        }
+        __syncthreads();
+        if (tid < 128) {
+            for (int p = 0; p < np; ++p) {
+                const int c = pstart[p];
+                const int w = (p + 1 < np ? pstart[p + 1] : end) - c;
+                int d = -1, sv = -1, t = 0;
+                if (tid < 2 * w) { d = sdst[2 * (c - start) + tid]; sv = ssrc[2 * (c - start) + tid]; }
+                const bool act = d >= 0 && d != sv;
+                if (act) t = cur[sv - start];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (act) cur[d - start] = t;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        __syncthreads();
+    } else {
     // sequential over panels, parallel within one: eight groups of 128 threads take the panels round-robin and keep
     // their next panel's entries prefetched, so the global-load latency hides behind the seven panels in between
     const int group = tid >> 7, e = tid & 127;
@@ -169,7 +195,7 @@ laswp_compose_kernel(const int *__restrict__ perm_dst, const int *__restrict__ p
         if (mine) prefetch(p + 8);
         __syncthreads();
     }
-    const int n1 = end - start;
+    }
     for (int i = tid; i < n1; i += kComposeThreads) srcmap[i] = cur[i];
     // below-block rows whose content changed: ordered compaction of (dst, src) pairs
     int total = 0;
@@ -281,11 +307,13 @@ int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64
         // node-level path: compose the panels' lists into the net permutation, then one pass per column
         const int64_t rounds = np <= cap ? 1 : (np + (cap - RFB_MAX_NB) - 1) / (cap - RFB_MAX_NB);
         const int64_t chunk = np < cap ? np : cap;                // upper bound of a chunk's pivot count
-        const size_t csmem = sizeof(int) * (size_t)(row_bound - k0);
+        size_t csmem = sizeof(int) * (size_t)(row_bound - k0);
+        const int stage_lists = csmem + 4 * sizeof(int) * (size_t)chunk <= sizeof(int) * (size_t)kNetMaxRows ? 1 : 0;
+        if (stage_lists) csmem += 4 * sizeof(int) * (size_t)chunk;
         RFB_TRY(rfb_ensure_smem(ctx, (const void *)laswp_compose_kernel, sizeof(int) * (size_t)kNetMaxRows));
         for (int64_t r = 0; r < rounds; ++r) {
             laswp_compose_kernel<<<1, kComposeThreads, csmem, ctx->stream>>>(ctx->perm_dst, ctx->perm_src, ctx->perm_width, (int)k0,
-                                                                            (int)k1, (int)row_bound, (int)cap, r == 0 ? 1 : 0, ctx->net_meta(),
+                                                                            (int)k1, (int)row_bound, (int)cap, r == 0 ? 1 : 0, stage_lists, ctx->net_meta(),
                                                                             ctx->net_srcmap(), ctx->net_clist(), &ctx->xchg->error_flag);
             RFB_CUDA(ctx, cudaGetLastError());
             ctx->launches++;

@@ -127,7 +127,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     // Float32 arithmetic of the trailing update: resolve RFB_F32_AUTO once per factorization (include/rfb200.h)
     rfb_opts resolved = opts ? *opts : rfb_opts{};
     if (sizeof(T) == 4 && resolved.f32_mode == RFB_F32_AUTO)
-        resolved.f32_mode = (m < n ? m : n) > 512 ? RFB_F32_TF32X3 : RFB_F32_FP32;
+        resolved.f32_mode = (m < n ? m : n) >= 4096 ? RFB_F32_TF32X3 : RFB_F32_FP32;
     opts = &resolved;
     plan.opts = opts;
     plan.up_events = up_events;

@@ -511,7 +511,7 @@ int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
     r->es = f32 ? 4 : 8;
     r->opts = rfb_opts{};
     r->opts.mem_space = RFB_MEM_DEVICE;
-    if (f32) r->opts.f32_mode = n > 512 ? RFB_F32_TF32X3 : RFB_F32_FP32;      // RFB_F32_AUTO, resolved like rfb_lu_f32 does
+    if (f32) r->opts.f32_mode = n >= 4096 ? RFB_F32_TF32X3 : RFB_F32_FP32;      // RFB_F32_AUTO, resolved like rfb_lu_f32 does
     const MgPlan &P = r->plan;
     r->own.clear();
     r->lcol.assign(P.nblk, -1);

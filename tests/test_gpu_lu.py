@@ -171,7 +171,7 @@ def test_baseline_config_16384_properties(ctx):
 
 @pytest.mark.parametrize("n", [300, 512, 2048, 4096])
 def test_f32_tensor_core_mode(ctx, n):
-    """Float32 LU with the trailing update on tcgen05 (f32_mode = TF32X3; the default above 512 columns).  Stated tolerance:
+    """Float32 LU with the trailing update on tcgen05 (f32_mode = TF32X3; the default from 4096 columns up).  Stated tolerance:
     the north_star bound ||PA-LU||_F/||A||_F <= 20*n*eps(Float32) (met with a ~500x margin), a residual
     within 6x of the exact-FP32 mode's (the tensor core accumulates with truncation), and -- inside the
     reference's own tested range n <= 300 -- the reference's inf-norm bound 20*n*eps as well."""
