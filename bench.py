@@ -507,6 +507,8 @@ def run_ours_dist(args, rank, world, local_rank):
     """N > 1: ONE matrix factored by all GPUs (1-D block-cyclic columns + NCCL panel broadcast, C++ driver behind
     rfb_mg_*).  torch.distributed (gloo, CPU tensors) is only the launcher-side plumbing: the 128-byte NCCL id, the
     barriers around the timed region and the max over ranks."""
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -514,7 +516,10 @@ def run_ours_dist(args, rank, world, local_rank):
     from rfb200.dist_lu import DistributedLU, block_range
 
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout; stdout carries ONE JSON line
+        # NCCL prints its version banner on stdout at VERSION and WARN; stdout carries ONE JSON line, so (unless the
+        # launcher asked for a specific debug level) warnings go to a per-process file instead
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rfb200_nccl_%h_%p.log")
     dist.init_process_group("gloo")
     n = args.n if args.n else 32768
     nb = args.block
@@ -580,6 +585,25 @@ def run_ours_dist(args, rank, world, local_rank):
     ms = max_over_ranks(sum(times) / len(times))
     value = lu_flops(n) / (ms * 1e-3) / 1e9
     info = d.info()
+
+    # ---- per-rank breakdown: host-scheduler statistics of the last timed step + one untimed pass with events around every launch ----
+    sched = d.sched_stats()
+    lib, hctx = d._lib, d.ctx_handle
+    restore()
+    dist.barrier()
+    lib.rfb_profile_enable(hctx, 1)
+    d.factor()
+    prof_wall = d.synchronize()
+    pms, pcnt, pwork = (C.c_double * 8)(), (C.c_int64 * 8)(), (C.c_double * 8)()
+    lib.rfb_profile_read(hctx, pms, pcnt, pwork)
+    lib.rfb_profile_enable(hctx, 0)
+    names = ["panel", "laswp", "trsm_diag", "gemm", "other"]
+    mine = {"rank": rank, "sched": sched, "profiled_pass_ms": prof_wall,
+            "kernel_ms": {nm: round(pms[i], 2) for i, nm in enumerate(names)},
+            "launches": {nm: int(pcnt[i]) for i, nm in enumerate(names)},
+            "gemm_tflops": round(pwork[3] / (pms[3] * 1e-3) / 1e12, 2) if pms[3] > 0 else None}
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, mine)
 
     # ---- distributed residual probe ||(PA - LU) x|| / ||A|| with +-1 probes (O(n^2) per rank) -----
     ipiv = d.pivots()
@@ -681,7 +705,7 @@ def run_ours_dist(args, rank, world, local_rank):
                          "peak": None, "unit": "TFLOP/s per GPU (whole LU, not the kernel alone)", "frac": None, "traffic": None,
                          "note": "per-kernel roofline is reported by the 1-GPU run; here NCCL bytes per rank = "
                                  f"{d.stats()['bcast_bytes_per_rank'] / max(1, args.steps + args.warmup + (0 if args.skip_e2e else 1 + min(args.steps, 2))) / 1e9:.2f} GB per factorization"},
-            "cpu_baseline": None, "checks": checks,
+            "cpu_baseline": None, "checks": checks, "per_rank": per_rank,
         }
         if single is not None:
             checks["pivots_equal_single_gpu"] = single["pivots_equal_single_gpu"]

@@ -239,6 +239,9 @@ int rfb_mg_sync(rfb_mg *mg, float *ms);        /* waits; *ms = device time of th
 int rfb_mg_get_pivots(rfb_mg *mg, int64_t *ipiv_host);               /* n pivots, 1-based global rows (every rank holds all) */
 int rfb_mg_get_info(rfb_mg *mg, int64_t *info);                      /* global info (collective in per-GPU handles)         */
 int rfb_mg_stats(rfb_mg *mg, int64_t *bcast_bytes_per_rank, int64_t *launches);
+/* host-scheduler statistics of local rank lr's last factorization: [0] bulk slices, [1] critical-path enqueues, [2] us with an idle
+ * compute stream and nothing runnable, [3] us of the whole schedule loop, [4] kernels launched so far */
+int rfb_mg_sched_stats(rfb_mg *mg, int lr, int64_t out[8]);
 int rfb_mg_lu_f64(rfb_mg *mg, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block);
 int rfb_mg_lu_f32(rfb_mg *mg, float *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block);
 int rfb_lu_f64_mg(const int *devices, int ngpus, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info,

@@ -95,6 +95,7 @@ SIGNATURES = {
     "rfb_mg_get_pivots": (_int, [_p, _p]),
     "rfb_mg_get_info": (_int, [_p, C.POINTER(_i64)]),
     "rfb_mg_stats": (_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "rfb_mg_sched_stats": (_int, [_p, _int, C.POINTER(_i64)]),
     "rfb_mg_lu_f64": (_int, [_p, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),
     "rfb_mg_lu_f32": (_int, [_p, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),
     "rfb_lu_f64_mg": (_int, [C.POINTER(_int), _int, _p, _i64, _i64, _p, C.POINTER(_i64), _i64]),

@@ -64,7 +64,8 @@ NcclApi *nccl_api() {
             if (api.handle) break;
         }
         if (!api.handle) { api.error = std::string("cannot load libnccl: ") + dlerror(); return; }
-        auto sym = [&](const char *n) { return dlsym(api.handle, n); };
+        // global scope first: a preloaded interposer (profilers, the harness' own NCCL hooks) must still see our calls
+        auto sym = [&](const char *n) { void *p = dlsym(RTLD_DEFAULT, n); return p ? p : dlsym(api.handle, n); };
 #define RFB_NCCL_SYM(field, name)                                                  \
         api.field = reinterpret_cast<decltype(api.field)>(sym(name));              \
         if (!api.field && api.error.empty()) api.error = std::string("libnccl lacks ") + name;
@@ -164,11 +165,20 @@ struct MgRank {
     std::vector<char> up_pending;
     cudaEvent_t ev_sent = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_final = nullptr, ev_chunk[2] = {nullptr, nullptr};
     rfb_opts opts = {};
-    int64_t kmax = 2048;            // bulk GEMM pieces: at most this many inner columns per launch (0 = never split k)
+    // Bulk-update slicing (set per problem by rank_setup from the bulk / critical-path balance, env overrides):
+    //   kmax        inner columns per GEMM launch (0 = never split k).  Fixed per problem: it decides the summation order.
+    //   piece_tiles 128 x 128 output tiles per GEMM launch (0 = never split rows); sm_count - 8 = one wave beside the
+    //               communication kernel's CTAs.  Row splitting does not change any result.
+    int64_t kmax = 2048;
+    int64_t piece_tiles = 140;
+    int64_t kmax_env = -1, piece_tiles_env = -1;
     double slice_us = 250.0;
     int status = RFB_OK;
     std::string error;
     int64_t bcast_bytes = 0;
+    // scheduler statistics of the last factorization (host side): slices, critical-path enqueues, time with nothing to enqueue
+    int64_t st_slices = 0, st_crit = 0, st_crit_late_us = 0;
+    double st_idle_us = 0, st_wall_us = 0;
     // dry run
     bool dry = false;
     std::vector<int64_t> *trace = nullptr;
@@ -214,12 +224,11 @@ struct MgRank {
 // ---- expansion of one update task U(node -> block j) into launch-level operations ----------------------------------------
 template <typename T>
 void emit_gemm(std::vector<MgOp> &ops, char *C, char *A, char *B, int64_t m, int64_t nn, int64_t k, int64_t lda, bool split,
-               int64_t kmax) {
+               int64_t kmax, int64_t piece_tiles) {
     if (m <= 0 || nn <= 0 || k <= 0) return;
-    const int64_t kstep = (split && kmax > 0) ? kmax : k;
+    const int64_t kstep = kmax > 0 ? kmax : k;        // (not conditional on `split`: the k cut decides the summation order)
     const int64_t tiles_n = (nn + 127) / 128;
-    // one-wave pieces: ~128 tiles of 128 x 128 fit beside the communication kernel's CTAs on 148 SMs
-    const int64_t rstep = split ? 128 * std::max<int64_t>(1, 128 / tiles_n) : m;
+    const int64_t rstep = (split && piece_tiles > 0) ? 128 * std::max<int64_t>(1, piece_tiles / tiles_n) : m;
     for (int64_t k0 = 0; k0 < k; k0 += kstep) {
         const int64_t kk = std::min(kstep, k - k0);
         for (int64_t r0 = 0; r0 < m; r0 += rstep) {
@@ -237,7 +246,8 @@ void emit_gemm(std::vector<MgOp> &ops, char *C, char *A, char *B, int64_t m, int
 }
 
 template <typename T>
-void emit_trsm(std::vector<MgOp> &ops, char *Lm, int64_t k, char *B, int64_t nrhs, int64_t lda, bool split, int64_t kmax) {
+void emit_trsm(std::vector<MgOp> &ops, char *Lm, int64_t k, char *B, int64_t nrhs, int64_t lda, bool split, int64_t kmax,
+               int64_t piece_tiles) {
     constexpr int64_t tb = 256;                              // the fused 256-row block solve (trsm.cu)
     if (k <= tb) {
         MgOp o{};
@@ -248,9 +258,10 @@ void emit_trsm(std::vector<MgOp> &ops, char *Lm, int64_t k, char *B, int64_t nrh
     }
     int64_t k1 = ((k / 2 + tb - 1) / tb) * tb;               // same split rule as trsm_rec
     if (k1 >= k) k1 = ((k - 1) / tb) * tb;
-    emit_trsm<T>(ops, Lm, k1, B, nrhs, lda, split, kmax);
-    emit_gemm<T>(ops, B + (size_t)k1 * sizeof(T), Lm + (size_t)k1 * sizeof(T), B, k - k1, nrhs, k1, lda, split, kmax);
-    emit_trsm<T>(ops, Lm + ((size_t)k1 + (size_t)k1 * (size_t)lda) * sizeof(T), k - k1, B + (size_t)k1 * sizeof(T), nrhs, lda, split, kmax);
+    emit_trsm<T>(ops, Lm, k1, B, nrhs, lda, split, kmax, piece_tiles);
+    emit_gemm<T>(ops, B + (size_t)k1 * sizeof(T), Lm + (size_t)k1 * sizeof(T), B, k - k1, nrhs, k1, lda, split, kmax, piece_tiles);
+    emit_trsm<T>(ops, Lm + ((size_t)k1 + (size_t)k1 * (size_t)lda) * sizeof(T), k - k1, B + (size_t)k1 * sizeof(T), nrhs, lda, split, kmax,
+                 piece_tiles);
 }
 
 template <typename T>
@@ -386,8 +397,9 @@ struct MgSched {
         s.kind = 0; s.p0 = r->Aj(c0, lc); s.a = w; s.b = c0; s.c = c0 + n1;
         s.est_us = 6.0 + 32.0 * (double)n1 * (double)w / 2.5e6;
         v.push_back(s);                                                                                  // :233
-        emit_trsm<T>(v, r->Lp(c0, c0), n1, r->Aj(c0, lc), w, P.n, split, r->kmax);                       // :235
-        emit_gemm<T>(v, r->Aj(c0 + n1, lc), r->Lp(c0 + n1, c0), r->Aj(c0, lc), P.n - c0 - n1, w, n1, P.n, split, r->kmax);   // :240
+        emit_trsm<T>(v, r->Lp(c0, c0), n1, r->Aj(c0, lc), w, P.n, split, r->kmax, r->piece_tiles);       // :235
+        emit_gemm<T>(v, r->Aj(c0 + n1, lc), r->Lp(c0 + n1, c0), r->Aj(c0, lc), P.n - c0 - n1, w, n1, P.n, split, r->kmax,
+                     r->piece_tiles);                                                                    // :240
     }
 
     // enqueue operations of block j's current task until `budget_us` of estimated work is out (or the task ends)
@@ -444,7 +456,12 @@ struct MgSched {
     int run() {
         using clock = std::chrono::steady_clock;
         auto last_progress = clock::now();
+        const auto t_begin = last_progress;
+        r->st_slices = r->st_crit = 0;
+        r->st_idle_us = 0;
         size_t own_pos = 0;                                          // index into r->own of the next block to factor
+        auto idle_since = clock::now();
+        bool idling = false;
         while (true) {
             MG_TRY(r, advance_comm());
             while (own_pos < r->own.size() && factored[r->own[own_pos]]) own_pos++;
@@ -457,8 +474,10 @@ struct MgSched {
             bool crit = true;
             for (int t = next_task[jn]; t < (int)P.anc[jn].size() && crit; ++t) crit = arrived(dep_block(P.anc[jn][t]));
             if (crit) {
+                if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
                 while (next_task[jn] < (int)P.anc[jn].size()) MG_TRY(r, advance_task(jn, 1e30));
                 MG_TRY(r, factor(jn));
+                r->st_crit++;
                 last_progress = clock::now();
                 continue;
             }
@@ -469,16 +488,20 @@ struct MgSched {
                 if (next_task[j] < (int)P.anc[j].size() && arrived(dep_block(P.anc[j][next_task[j]]))) { pick = j; break; }
             }
             if (pick >= 0 && (r->dry || chunks_in_flight() < 2)) {
+                if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
                 MG_TRY(r, advance_task(pick, r->slice_us));
                 if (!r->dry) { MG_CUDA(r, cudaEventRecord(r->ev_chunk[chunks & 1], r->s_comp)); chunks++; }
+                r->st_slices++;
                 last_progress = clock::now();
                 continue;
             }
+            if (pick < 0 && !idling && !r->dry && chunks_in_flight() == 0) { idling = true; idle_since = clock::now(); }   // nothing to run at all
             if (r->dry) return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule cannot make progress (block %d)", jn);
             if (std::chrono::duration<double>(clock::now() - last_progress).count() > 60.0)
                 return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule stalled for 60 s waiting for block %d (rank %d)", jn, r->rank);
             std::this_thread::yield();
         }
+        r->st_wall_us = std::chrono::duration<double, std::micro>(clock::now() - t_begin).count();
         return RFB_OK;
     }
 };
@@ -509,6 +532,19 @@ int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
     r->plan.build(n, nb, r->world);
     r->f32 = f32;
     r->es = f32 ? 4 : 8;
+    {
+        // balance of this problem on this many ranks: bulk = all GEMM-shaped work of one rank at a typical rate, critical path =
+        // every block column's pivot chain (one all-CTA exchange per column) + its in-block updates, broadcast and hand-over
+        const double t_bulk = (2.0 / 3.0) * (double)n * (double)n * (double)n / r->world / (f32 ? 60e12 : 28e12);
+        const double t_crit = (double)r->plan.nblk * ((double)nb * 2.4e-6 + 1.2e-3);
+        const double ratio = t_bulk / t_crit;
+        const int64_t wave = std::max(32, r->ctx->sm_count - 8);
+        if (ratio > 1.5) { r->kmax = 0; r->piece_tiles = 0; }                 // bulk-bound: whole GEMMs, the pivot chain has slack
+        else if (ratio > 0.8) { r->kmax = 4096; r->piece_tiles = 2 * wave; }
+        else { r->kmax = 2048; r->piece_tiles = wave; }                        // critical-path-bound: one-wave pieces, <= 0.3 ms each
+        if (r->kmax_env >= 0) r->kmax = r->kmax_env;
+        if (r->piece_tiles_env >= 0) r->piece_tiles = r->piece_tiles_env;
+    }
     r->opts = rfb_opts{};
     r->opts.mem_space = RFB_MEM_DEVICE;
     if (f32) r->opts.f32_mode = n >= 4096 ? RFB_F32_TF32X3 : RFB_F32_FP32;      // RFB_F32_AUTO, resolved like rfb_lu_f32 does
@@ -564,7 +600,8 @@ int rank_create(MgRank *r) {
     MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_chunk[1], cudaEventDisableTiming));
     MG_CUDA(r, cudaEventCreate(&r->ev_t0));
     MG_CUDA(r, cudaEventCreate(&r->ev_t1));
-    if (const char *e = getenv("RFB_MG_KMAX")) r->kmax = atoll(e);
+    if (const char *e = getenv("RFB_MG_KMAX")) r->kmax_env = atoll(e);
+    if (const char *e = getenv("RFB_MG_PIECE_TILES")) r->piece_tiles_env = atoll(e);
     if (const char *e = getenv("RFB_MG_SLICE_US")) r->slice_us = atof(e);
     return RFB_OK;
 }
@@ -907,6 +944,18 @@ int rfb_mg_stats(rfb_mg *mg, int64_t *bcast_bytes_per_rank, int64_t *launches) {
     if (!r) return RFB_ERR_ARG;
     if (bcast_bytes_per_rank) *bcast_bytes_per_rank = r->bcast_bytes;
     if (launches) { int64_t s = 0; for (MgRank *q : mg->ranks) s += q->ctx->launches; *launches = s; }
+    return RFB_OK;
+}
+
+// scheduler statistics of local rank lr's last factorization: out[0] bulk slices enqueued, out[1] critical-path enqueues (own
+// block columns), out[2] host microseconds with an idle compute stream and nothing runnable, out[3] host microseconds of the whole
+// schedule loop, out[4] kernels launched so far by the rank's context
+int rfb_mg_sched_stats(rfb_mg *mg, int lr, int64_t out[8]) {
+    MgRank *r = local(mg, lr);
+    if (!r || !out) return RFB_ERR_ARG;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    out[0] = r->st_slices; out[1] = r->st_crit; out[2] = (int64_t)r->st_idle_us; out[3] = (int64_t)r->st_wall_us;
+    out[4] = r->ctx ? r->ctx->launches : 0;
     return RFB_OK;
 }
 

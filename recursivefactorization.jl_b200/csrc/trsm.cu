@@ -183,48 +183,80 @@ __device__ __forceinline__ void trsm_cp_async8(double *dst, const double *src, i
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
 }
 
+__device__ __forceinline__ void trsm_cp_async16(double *dst, const double *src, int src_bytes) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// W consumer warps (8 right-hand-side columns each) + ONE producer warp that does nothing but stream the 64 x 64 tiles
+// of L into the double buffer (v1 let the consumers copy: more than half of their instructions were address arithmetic
+// of the copy loop, profiles/r02_trsm_dmma_kernel_v1.txt).
 template <int W>
-__global__ void __launch_bounds__(W * 32)
-trsm_dmma_kernel(const double *__restrict__ L, int kb, double *__restrict__ B, long long nrhs, long long lda) {
+__global__ void __launch_bounds__((W + 1) * 32)
+trsm_dmma_kernel(const double *__restrict__ L, int kb, double *__restrict__ B, long long nrhs, long long lda, int aligned16) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sL = reinterpret_cast<double *>(smem_raw);               // [2][64 cols][kLdTile]
     double *sXall = sL + 2 * 64 * kLdTile;                           // [W][4 sub-blocks][64 rows][8 cols], NEGATED unknowns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == W;
     const int g = lane >> 2, q = lane & 3;
-    double *sx = sXall + warp * (4 * 64 * 8);
+    double *sx = sXall + (producer ? 0 : warp) * (4 * 64 * 8);
     const long long col0 = (long long)blockIdx.x * (W * 8) + warp * 8;
     const int nsub = (kb + 63) >> 6;
     const int ntiles = nsub * (nsub + 1) / 2;
 
-    auto load_tile = [&](int s, int t, int buf) {
+    auto load_tile = [&](int s, int t, int buf) {                    // producer warp only
         double *dstb = sL + buf * 64 * kLdTile;
-        for (int e = tid; e < 64 * 64; e += W * 32) {
-            const int r = e & 63, c = e >> 6;
-            const int gr = s * 64 + r, gc = t * 64 + c;
-            const bool ok = gr < kb && gc < kb;
-            trsm_cp_async8(dstb + c * kLdTile + r, L + (ok ? (long long)gr + (long long)gc * lda : 0), ok ? 8 : 0);
+        if (aligned16) {                                             // lane = row pair, one 16-byte copy per column
+            const int r = 2 * lane, gr = s * 64 + r;
+            const double *src = L + gr + (long long)(t * 64) * lda;
+            const int rb = gr + 1 < kb ? 16 : (gr < kb ? 8 : 0);
+#pragma unroll 8
+            for (int c = 0; c < 64; ++c)
+                trsm_cp_async16(dstb + c * kLdTile + r, rb && t * 64 + c < kb ? src + (long long)c * lda : L, t * 64 + c < kb ? rb : 0);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = lane + 32 * h, gr = s * 64 + r;
+                const double *src = L + gr + (long long)(t * 64) * lda;
+#pragma unroll 8
+                for (int c = 0; c < 64; ++c) {
+                    const bool ok = gr < kb && t * 64 + c < kb;
+                    trsm_cp_async8(dstb + c * kLdTile + r, ok ? src + (long long)c * lda : L, ok ? 8 : 0);
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-
-    load_tile(0, 0, 0);
-    int idx = 0;
-    for (int s = 0; s < nsub; ++s) {
-        double xc[8][2];
+    auto load_x = [&](int s, double (&x)[8][2]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int row = s * 64 + 8 * i + g;
                 const long long col = col0 + 2 * q + e;
-                xc[i][e] = (row < kb && col < nrhs) ? B[row + col * lda] : 0.0;
+                x[i][e] = (row < kb && col < nrhs) ? B[row + col * lda] : 0.0;
             }
+    };
+
+    if (producer) load_tile(0, 0, 0);
+    double xc[8][2], xn[8][2];
+    if (!producer) load_x(0, xn);
+    int idx = 0;
+    for (int s = 0; s < nsub; ++s) {
+        if (!producer) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { xc[i][0] = xn[i][0]; xc[i][1] = xn[i][1]; }
+        }
         for (int t = 0; t <= s; ++t, ++idx) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (producer) asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();                                   // tile idx has landed; every warp is done with tile idx - 1
-            if (idx + 1 < ntiles) {
-                const int s2 = (t == s) ? s + 1 : s, t2 = (t == s) ? 0 : t + 1;
-                load_tile(s2, t2, (idx + 1) & 1);
+            if (producer) {
+                if (idx + 1 < ntiles) {
+                    const int s2 = (t == s) ? s + 1 : s, t2 = (t == s) ? 0 : t + 1;
+                    load_tile(s2, t2, (idx + 1) & 1);
+                }
+                continue;
             }
             const double *tL = sL + (idx & 1) * 64 * kLdTile;
             if (t < s) {                                       // x_s -= L_st x_t
@@ -237,6 +269,7 @@ trsm_dmma_kernel(const double *__restrict__ L, int kb, double *__restrict__ B, l
                     for (int i = 0; i < 8; ++i) trsm_dmma(xc[i][0], xc[i][1], ta[8 * i], b);
                 }
             } else {                                           // the 64 x 64 unit-lower triangle
+                if (s + 1 < nsub) load_x(s + 1, xn);           // next sub-block's right-hand sides fly during this triangle
                 double *xs = sx + s * (64 * 8);
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
@@ -285,7 +318,8 @@ int launch_dmma(rfb_ctx *ctx, const double *L, int kb, double *B, int64_t nrhs, 
     auto kern = trsm_dmma_kernel<W>;
     RFB_TRY(rfb_ensure_smem(ctx, (const void *)kern, smem));
     RfbLaunchScope scope(ctx, RFB_KC_TRSM, (double)kb * (double)kb * (double)nrhs);
-    kern<<<(unsigned int)((nrhs + W * 8 - 1) / (W * 8)), W * 32, smem, ctx->stream>>>(L, kb, B, nrhs, lda);
+    const int aligned16 = ((reinterpret_cast<uintptr_t>(L) & 15) == 0 && (lda & 1) == 0) ? 1 : 0;
+    kern<<<(unsigned int)((nrhs + W * 8 - 1) / (W * 8)), (W + 1) * 32, smem, ctx->stream>>>(L, kb, B, nrhs, lda, aligned16);
     RFB_CUDA(ctx, cudaGetLastError());
     return RFB_OK;
 }
@@ -304,6 +338,9 @@ int launch_block(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t l
     }
     return launch_block_legacy<T>(ctx, L, kb, B, nrhs, lda);
 }
+
+
+
 
 template <typename T>
 int launch_block_legacy(rfb_ctx *ctx, const T *L, int kb, T *B, int64_t nrhs, int64_t lda) {

@@ -85,6 +85,11 @@ class _MgHandle:
         self._check(self._lib.rfb_mg_sync(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def sched_stats(self, lr: int = 0) -> dict:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.rfb_mg_sched_stats(self._h, lr, out))
+        return {"bulk_slices": out[0], "critical_enqueues": out[1], "host_idle_ms": out[2] / 1e3, "schedule_loop_ms": out[3] / 1e3}
+
     def stats(self) -> dict:
         b, l = C.c_int64(), C.c_int64()
         self._check(self._lib.rfb_mg_stats(self._h, C.byref(b), C.byref(l)))

@@ -36,7 +36,7 @@ def main(rep, out):
     if len(rows) > 2:
         hdr = rows[1]
         si, ni, ei = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-        data = [(int(r[ni] or 0), r[si].strip(), r[ei]) for r in rows[2:] if len(r) > ni]
+        data = [(int(r[ni] or 0), r[si].strip(), r[ei]) for r in rows[2:] if len(r) > ni and (r[ni] or "0").isdigit()]
         tot = sum(d[0] for d in data) or 1
         lines.append("")
         lines.append(f"## top stall-sample SASS instructions of the first captured launch ({tot} samples, {len(data)} instructions)")
