@@ -171,6 +171,7 @@ struct MgRank {
     //               communication kernel's CTAs.  Row splitting does not change any result.
     int64_t kmax = 2048;
     int64_t piece_tiles = 140;
+    int merge_blocks = 1, merge_env = -1;   // owned block columns one bulk task may cover (see MgSched::build_task)
     int64_t kmax_env = -1, piece_tiles_env = -1;
     double slice_us = 250.0;
     int status = RFB_OK;
@@ -287,6 +288,10 @@ struct MgSched {
     std::vector<std::vector<MgOp>> ops;        // own blocks: operations of the task in progress
     std::vector<size_t> op_pos;
     std::vector<char> touched;
+    // A bulk task may cover SEVERAL consecutive owned block columns that wait for the same node's update (they are adjacent in
+    // the rank's compact storage): one swap / TRSM / GEMM sequence with nrhs = the sum of their widths instead of one latency
+    // chain of diagonal blocks per 512 columns.  gcount[leader] = blocks in the task in progress, follower_of[j] = its leader.
+    std::vector<int> gcount, follower_of;
     int chunks = 0;
 
     explicit MgSched(MgRank *rank) : r(rank), P(rank->plan) {
@@ -295,6 +300,8 @@ struct MgSched {
         ops.assign(P.nblk, {});
         op_pos.assign(P.nblk, 0);
         touched.assign(P.nblk, 0);
+        gcount.assign(P.nblk, 1);
+        follower_of.assign(P.nblk, -1);
     }
 
     int dep_block(int node) const { return P.nodes[node].b0 + P.nodes[node].nb1 - 1; }   // last block of the node's left half
@@ -385,11 +392,22 @@ struct MgSched {
     }
 
     // ---- compute stream -----------------------------------------------------------------------------------------------
-    void build_task(int j) {
+    void build_task(int j, bool merge) {
         const int id = P.anc[j][next_task[j]];
         const MgNode &N = P.nodes[id];
-        const int64_t c0 = P.col0(N.b0), n1 = (int64_t)N.nb1 * P.nb, w = P.width(j), lc = r->lcol[j];
-        const bool split = next_task[j] + 1 < (int)P.anc[j].size();      // the lowest update runs on the critical path: whole launches
+        const int64_t c0 = P.col0(N.b0), n1 = (int64_t)N.nb1 * P.nb, lc = r->lcol[j];
+        int64_t w = P.width(j);
+        gcount[j] = 1;
+        if (merge) {       // the following owned block columns whose next pending update is this same node
+            for (int j2 = j + P.world; j2 < P.nblk; j2 += P.world) {
+                if (gcount[j] >= r->merge_blocks) break;
+                if (next_task[j2] >= (int)P.anc[j2].size() || P.anc[j2][next_task[j2]] != id || !ops[j2].empty() || follower_of[j2] >= 0) break;
+                follower_of[j2] = j;
+                gcount[j]++;
+                w += P.width(j2);
+            }
+        }
+        const bool split = merge || next_task[j] + 1 < (int)P.anc[j].size();   // the lowest update alone runs on the critical path: whole launches
         std::vector<MgOp> &v = ops[j];
         v.clear();
         op_pos[j] = 0;
@@ -403,7 +421,7 @@ struct MgSched {
     }
 
     // enqueue operations of block j's current task until `budget_us` of estimated work is out (or the task ends)
-    int advance_task(int j, double budget_us) {
+    int advance_task(int j, double budget_us, bool merge) {
         if (r->dry) {
             const MgNode &N = P.nodes[P.anc[j][next_task[j]]];
             r->rec(MG_T_UPDATE, P.col0(N.b0), (int64_t)N.nb1 * P.nb, j, 0);
@@ -411,10 +429,11 @@ struct MgSched {
             return RFB_OK;
         }
         if (ops[j].empty()) {
-            build_task(j);
-            if (!touched[j]) {
-                touched[j] = 1;
-                if (r->up_pending[j]) { MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_up[j], 0)); r->up_pending[j] = 0; }
+            build_task(j, merge);
+            for (int g = 0, jj = j; g < gcount[j]; ++g, jj += P.world) {
+                if (touched[jj]) continue;
+                touched[jj] = 1;
+                if (r->up_pending[jj]) { MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_up[jj], 0)); r->up_pending[jj] = 0; }
             }
             MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_blk[dep_block(P.anc[j][next_task[j]])], 0));
         }
@@ -424,7 +443,11 @@ struct MgSched {
             MG_TRY(r, run_op<T>(r, o));
             out += o.est_us;
         }
-        if (op_pos[j] >= ops[j].size()) { ops[j].clear(); next_task[j]++; }
+        if (op_pos[j] >= ops[j].size()) {
+            ops[j].clear();
+            for (int g = 0, jj = j; g < gcount[j]; ++g, jj += P.world) { next_task[jj]++; follower_of[jj] = -1; }
+            gcount[j] = 1;
+        }
         return RFB_OK;
     }
 
@@ -475,7 +498,7 @@ struct MgSched {
             for (int t = next_task[jn]; t < (int)P.anc[jn].size() && crit; ++t) crit = arrived(dep_block(P.anc[jn][t]));
             if (crit) {
                 if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
-                while (next_task[jn] < (int)P.anc[jn].size()) MG_TRY(r, advance_task(jn, 1e30));
+                while (next_task[jn] < (int)P.anc[jn].size()) MG_TRY(r, advance_task(jn, 1e30, false));
                 MG_TRY(r, factor(jn));
                 r->st_crit++;
                 last_progress = clock::now();
@@ -485,11 +508,12 @@ struct MgSched {
             int pick = -1;
             for (size_t q = own_pos; q < r->own.size(); ++q) {
                 const int j = r->own[q];
+                if (follower_of[j] >= 0) continue;                 // rides in a merged task led by an earlier block column
                 if (next_task[j] < (int)P.anc[j].size() && arrived(dep_block(P.anc[j][next_task[j]]))) { pick = j; break; }
             }
             if (pick >= 0 && (r->dry || chunks_in_flight() < 2)) {
                 if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
-                MG_TRY(r, advance_task(pick, r->slice_us));
+                MG_TRY(r, advance_task(pick, r->slice_us, true));
                 if (!r->dry) { MG_CUDA(r, cudaEventRecord(r->ev_chunk[chunks & 1], r->s_comp)); chunks++; }
                 r->st_slices++;
                 last_progress = clock::now();
@@ -539,9 +563,12 @@ int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
         const double t_crit = (double)r->plan.nblk * ((double)nb * 2.4e-6 + 1.2e-3);
         const double ratio = t_bulk / t_crit;
         const int64_t wave = std::max(32, r->ctx->sm_count - 8);
-        if (ratio > 1.5) { r->kmax = 0; r->piece_tiles = 0; }                 // bulk-bound: whole GEMMs, the pivot chain has slack
-        else if (ratio > 0.8) { r->kmax = 4096; r->piece_tiles = 2 * wave; }
+        if (ratio > 0.8) { r->kmax = 4096; r->piece_tiles = 2 * wave; }       // bulk-bound: two-wave pieces (~1 ms), the pivot chain has slack
         else { r->kmax = 2048; r->piece_tiles = wave; }                        // critical-path-bound: one-wave pieces, <= 0.3 ms each
+        // merging amortises the per-task latency chain (n1 / 256 dependent diagonal blocks + as many small GEMMs, ~4 ms at the
+        // root) over more columns, but the first block column of a merged task is only ready when the whole task is
+        r->merge_blocks = ratio > 2.0 ? 4 : (ratio > 0.8 ? 2 : 1);
+        if (r->merge_env > 0) r->merge_blocks = r->merge_env;
         if (r->kmax_env >= 0) r->kmax = r->kmax_env;
         if (r->piece_tiles_env >= 0) r->piece_tiles = r->piece_tiles_env;
     }
@@ -602,6 +629,7 @@ int rank_create(MgRank *r) {
     MG_CUDA(r, cudaEventCreate(&r->ev_t1));
     if (const char *e = getenv("RFB_MG_KMAX")) r->kmax_env = atoll(e);
     if (const char *e = getenv("RFB_MG_PIECE_TILES")) r->piece_tiles_env = atoll(e);
+    if (const char *e = getenv("RFB_MG_MERGE")) r->merge_env = atoi(e);
     if (const char *e = getenv("RFB_MG_SLICE_US")) r->slice_us = atof(e);
     return RFB_OK;
 }
