@@ -228,6 +228,7 @@ int rfb_mg_create_all(rfb_mg **out, int ngpus, const int *devices);
 int rfb_mg_destroy(rfb_mg *mg);
 const char *rfb_mg_last_error(rfb_mg *mg);
 int rfb_mg_setup(rfb_mg *mg, int64_t n, int64_t block, int is_f32);  /* (re)allocates replica + own block columns       */
+int rfb_mg_owner_of(int64_t block, int world);                       /* rank that owns block column `block` (no handle needed) */
 int rfb_mg_local_ranks(rfb_mg *mg, int *count, int *world);
 int rfb_mg_rank_ctx(rfb_mg *mg, int lr, rfb_ctx **ctx, int *global_rank);   /* the rank's single-GPU context (same device) */
 int rfb_mg_block_ptr(rfb_mg *mg, int lr, int64_t j, void **dev_ptr); /* owned block column j: n x w, leading dimension n */
@@ -240,7 +241,8 @@ int rfb_mg_get_pivots(rfb_mg *mg, int64_t *ipiv_host);               /* n pivots
 int rfb_mg_get_info(rfb_mg *mg, int64_t *info);                      /* global info (collective in per-GPU handles)         */
 int rfb_mg_stats(rfb_mg *mg, int64_t *bcast_bytes_per_rank, int64_t *launches);
 /* host-scheduler statistics of local rank lr's last factorization: [0] bulk slices, [1] critical-path enqueues, [2] us with an idle
- * compute stream and nothing runnable, [3] us of the whole schedule loop, [4] kernels launched so far */
+ * compute stream and nothing runnable, [3] us of the whole schedule loop, [4] kernels launched so far, [5] device us inside the
+ * owned block columns' critical sections (last contributions + factorization), [6] device us of their publications */
 int rfb_mg_sched_stats(rfb_mg *mg, int lr, int64_t out[8]);
 int rfb_mg_lu_f64(rfb_mg *mg, double *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block);
 int rfb_mg_lu_f32(rfb_mg *mg, float *A_host, int64_t n, int64_t lda, int64_t *ipiv, int64_t *info, int64_t block);

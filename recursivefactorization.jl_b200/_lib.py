@@ -85,6 +85,7 @@ SIGNATURES = {
     "rfb_mg_destroy": (_int, [_p]),
     "rfb_mg_last_error": (C.c_char_p, [_p]),
     "rfb_mg_setup": (_int, [_p, _i64, _i64, _int]),
+    "rfb_mg_owner_of": (_int, [_i64, _int]),
     "rfb_mg_local_ranks": (_int, [_p, C.POINTER(_int), C.POINTER(_int)]),
     "rfb_mg_rank_ctx": (_int, [_p, _int, C.POINTER(_p), C.POINTER(_int)]),
     "rfb_mg_block_ptr": (_int, [_p, _int, _i64, C.POINTER(_p)]),

@@ -297,7 +297,8 @@ static int launch_net(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int abs_ro
 
 // `row_bound`: one past the last absolute row any list of [k0, k1) can name (the root's row count, or lda).
 template <typename T>
-int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1, int64_t row_bound) {
+int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1, int64_t row_bound,
+                           int64_t cache_key) {
     if (ncols <= 0 || k1 <= k0) return RFB_OK;
     if (ctx->dry_run) { ctx->rec(RFB_T_LASWP, A, nullptr, nullptr, ncols, k0, k1); return RFB_OK; }
     const int64_t np = k1 - k0;
@@ -311,12 +312,20 @@ int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64
         const int stage_lists = csmem + 4 * sizeof(int) * (size_t)chunk <= sizeof(int) * (size_t)kNetMaxRows ? 1 : 0;
         if (stage_lists) csmem += 4 * sizeof(int) * (size_t)chunk;
         RFB_TRY(rfb_ensure_smem(ctx, (const void *)laswp_compose_kernel, sizeof(int) * (size_t)kNetMaxRows));
+        // `cache_key` >= 0 (single-chunk ranges only): the composition of this lane is kept and reused by later calls with the
+        // same key -- the multi-GPU driver applies one block column's pivots to many column groups, one composition serves all
+        const bool cached = cache_key >= 0 && rounds == 1 && ctx->net_key[ctx->lane] == cache_key;
+        if (!(cache_key >= 0 && rounds == 1)) ctx->net_key[ctx->lane] = -1;
         for (int64_t r = 0; r < rounds; ++r) {
-            laswp_compose_kernel<<<1, kComposeThreads, csmem, ctx->stream>>>(ctx->perm_dst, ctx->perm_src, ctx->perm_width, (int)k0,
-                                                                            (int)k1, (int)row_bound, (int)cap, r == 0 ? 1 : 0, stage_lists, ctx->net_meta(),
-                                                                            ctx->net_srcmap(), ctx->net_clist(), &ctx->xchg->error_flag);
-            RFB_CUDA(ctx, cudaGetLastError());
-            ctx->launches++;
+            if (!cached) {
+                laswp_compose_kernel<<<1, kComposeThreads, csmem, ctx->stream>>>(ctx->perm_dst, ctx->perm_src, ctx->perm_width, (int)k0,
+                                                                                (int)k1, (int)row_bound, (int)cap, r == 0 ? 1 : 0, stage_lists,
+                                                                                ctx->net_meta(), ctx->net_srcmap(), ctx->net_clist(),
+                                                                                &ctx->xchg->error_flag);
+                RFB_CUDA(ctx, cudaGetLastError());
+                ctx->launches++;
+                if (cache_key >= 0 && rounds == 1) ctx->net_key[ctx->lane] = cache_key;
+            }
             int rc;
             if (chunk <= 256) rc = launch_net<T, 256, 256, 1>(ctx, A, ncols, lda, (int)k0);
             else if (chunk <= 512) rc = launch_net<T, 256, 256, 2>(ctx, A, ncols, lda, (int)k0);
@@ -345,5 +354,5 @@ int rfb_launch_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t sh
 
 template int rfb_launch_laswp<double>(rfb_ctx *, double *, int64_t, int64_t, const int64_t *, int64_t, int64_t);
 template int rfb_launch_laswp<float>(rfb_ctx *, float *, int64_t, int64_t, const int64_t *, int64_t, int64_t);
-template int rfb_launch_laswp_lists<double>(rfb_ctx *, double *, int64_t, int64_t, int64_t, int64_t, int64_t);
-template int rfb_launch_laswp_lists<float>(rfb_ctx *, float *, int64_t, int64_t, int64_t, int64_t, int64_t);
+template int rfb_launch_laswp_lists<double>(rfb_ctx *, double *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t);
+template int rfb_launch_laswp_lists<float>(rfb_ctx *, float *, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t);

@@ -73,9 +73,11 @@ struct rfb_ctx {
     bool perm_external = false;           // arrays belong to the caller (rfb_perm_buffers)
     // node-level row interchange (laswp.cu): net permutation of the chunk being applied
     // (one set per lane: the multi-GPU driver runs interchanges on its compute stream and on its replica stream at once)
-    static constexpr int kLanes = 2;
+    // lanes 0 / 1: the two streams of a driver; lanes 2..: cached compositions of the multi-GPU driver (one per ring slot)
+    static constexpr int kLanes = 10;
     int lane = 0;
-    int *net_meta_[kLanes] = {nullptr, nullptr}, *net_srcmap_[kLanes] = {nullptr, nullptr}, *net_clist_[kLanes] = {nullptr, nullptr};
+    int *net_meta_[kLanes] = {}, *net_srcmap_[kLanes] = {}, *net_clist_[kLanes] = {};
+    int64_t net_key[kLanes] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
     int *net_meta() const { return net_meta_[lane]; }
     int *net_srcmap() const { return net_srcmap_[lane]; }
     int *net_clist() const { return net_clist_[lane]; }
@@ -200,7 +202,8 @@ int rfb_panel_leaf_for_rows(rfb_ctx *ctx, int64_t m);
 // list-driven row interchange: applies the exchange lists of the panels covering pivots [k0, k1)
 // to the (rows >= k0) x ncols block whose first row is absolute row k0
 template <typename T>
-int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1, int64_t row_bound);
+int rfb_launch_laswp_lists(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, int64_t k0, int64_t k1, int64_t row_bound,
+                           int64_t cache_key = -1);
 template <typename T>
 int rfb_launch_laswp(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv_dev,
                      int64_t npiv, int64_t ipiv_sub);

@@ -1,27 +1,35 @@
 // rfb_mg.cu -- multi-GPU recursive LU behind the C ABI (SURVEY.md section 8b "rfb_lu_f64_mg", section 8e).
 //
-// The reference has no distributed path; this is the same Toledo recursion (src/lu.jl:189-263) run over BLOCK
-// COLUMNS distributed 1-D block-cyclic over G GPUs of one node:
-//   * block column J (width nb) is owned by rank J mod G; a recursion node that is one block column is factored by its
-//     owner with the single-GPU path (reckernel! on the column range, rfb_lu_range), then the factored panel (rows below
-//     its diagonal block included) + its pivots + its row-exchange lists are broadcast from the owner with ncclBroadcast;
-//   * every rank keeps a full-size replica of L (valid where panels were received), so steps 2-4 of the recursion
-//     (row swaps :233, TRSM :235, Schur update :240) touch only columns the rank owns and need no communication;
-//     step 6 (:246, A21 <- P2 A21) is applied to the replica on every rank.
+// The reference has no distributed path.  Here ONE n x n matrix is factored by G GPUs of one node:
+//   * block columns of width nb are distributed 1-D block-cyclic (block column J on rank J mod G);
+//   * a block column is factored by its owner with the single-GPU path -- reckernel! (src/lu.jl:189-263) on the column
+//     range, rfb_lu_range -- i.e. the Toledo recursion runs INSIDE every block column;
+//   * the factored panel (rows below its diagonal block included) + its pivots + its row-exchange lists are broadcast from
+//     the owner with ncclBroadcast, one collective per block column;
+//   * ACROSS block columns the order is right-looking: when panel b has arrived, every rank applies b's step of
+//     reckernel! to the block columns it owns to the right of b -- row swaps (:233), A12 <- L11^-1 A12 (:235),
+//     A22 -= L21 A12 (:240) -- and b's pivots to its own finished columns on the left (:246).
 //
-// What is different from round 1 (a Python schedule on one stream per rank):
-//   * the schedule is C++, behind the C ABI; no torch / Python in the product path.  Two ways in: one process with G
-//     devices (rfb_mg_create_all: ncclCommInitRank per device inside one group, one host thread per device) -- what a
-//     Julia caller of lu! uses -- or one process per GPU (rfb_mg_create_rank with a shared ncclUniqueId) -- what
-//     torchrun / bench.py uses.  libnccl is loaded with dlopen, so the single-GPU library has no NCCL dependency.
-//   * communication has its own (high-priority) stream per rank: pack -> ncclBroadcast -> unpack -> replica swaps run
-//     there, ordered against the compute stream by events, so a rank's GEMMs overlap its own broadcasts.
-//   * updates are per (node, block column) tasks and are ordered by NEED, not by recursion order: the task list of an
-//     owned block column is "all ancestors' updates, top-down, then factor".  A host scheduler per rank keeps the
-//     compute stream fed: when everything the next owned block column waits for has ARRIVED (event query), its
-//     remaining updates + its factorization go out back to back (the critical path); otherwise a bounded slice
-//     (~0.3 ms) of the most urgent update whose inputs have arrived.  Long GEMMs are cut into one-wave pieces (rows and
-//     k) so the critical path never waits for more than two slices.
+// Round 1 ran the Toledo recursion over block columns as well (node-level TRSM / GEMM with the whole left half as the
+// inner dimension).  Measured on 8 GPUs (profiles/r02_bench_dist8gpu_32768_tree_schedule.json) that costs the critical
+// path dearly: the update of the first block column of a node's right half has the node's whole left half as inner
+// dimension (up to n/2 columns, a chain of n1/256 dependent diagonal solves) and cannot start before the left half's LAST
+// panel has arrived, and every per-block-column TRSM repeats that latency chain.  In the right-looking order only panel
+// b's own contribution (inner dimension nb) sits between the arrival of panel b and the factorization of block column
+// b + 1; the pivots are the same (same exact-arithmetic algorithm), the summation is grouped by block column.
+// It also needs no n x n replica of L: received panels live in a small ring.
+//
+// What runs where:
+//   * the schedule is C++, behind the C ABI; no torch / Python in the product path.  Two ways in: one process with G devices
+//     (rfb_mg_create_all: ncclCommInitRank per device inside one group, one host thread per device) -- what a Julia caller of
+//     lu! uses -- or one process per GPU (rfb_mg_create_rank with a shared ncclUniqueId) -- what torchrun / bench.py uses.
+//     libnccl is loaded with dlopen, so the single-GPU library has no NCCL dependency.
+//   * communication has its own (high-priority) stream per rank: pack -> ncclBroadcast -> unpack into the ring run there,
+//     ordered against the compute stream by events, so a rank's GEMMs overlap its own broadcasts.
+//   * a host scheduler per rank keeps the compute stream fed by NEED: when panel j - 1 has ARRIVED (event query) and the rank
+//     owns block column j, the contributions block column j still lacks and its factorization go out back to back (the
+//     critical path, look-ahead); otherwise a bounded slice (~0.5 ms) of the oldest pending contribution to the owned block
+//     columns nearest to the critical path, at most two slices in flight.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -84,51 +92,26 @@ NcclApi *nccl_api() {
     return &api;
 }
 
-// ---- the block-column recursion tree (pure host logic; shared by the GPU run and the dry-run trace) ------------------------
-struct MgNode {
-    int b0, nbk, nb1;     // blocks [b0, b0 + nbk), left half [b0, b0 + nb1)
-};
-
+// ---- the block-column layout (pure host logic; shared by the GPU run and the dry-run trace) ------------------------------------
 struct MgPlan {
     int64_t n = 0, nb = 0;
     int nblk = 0, world = 1;
-    std::vector<MgNode> nodes;
-    std::vector<std::vector<int>> anc;       // anc[j]: nodes (top-down) whose RIGHT half holds block j -> the updates block j receives
-    std::vector<std::vector<int>> ends_at;   // ends_at[e]: nodes whose last block is e, innermost first -> A21 <- P2 A21 (:246) points
-
     int64_t col0(int b) const { return (int64_t)b * nb; }
     int64_t width(int b) const { return std::min<int64_t>(n, (int64_t)(b + 1) * nb) - (int64_t)b * nb; }
-    int owner(int b) const { return b % world; }
-
-    void build_rec(int b0, int nbk) {
-        if (nbk <= 1) return;
-        const int nb1 = (nbk + 1) / 2;                 // block analogue of nsplit (src/lu.jl:158-162)
-        const int id = (int)nodes.size();
-        nodes.push_back({b0, nbk, nb1});
-        for (int j = b0 + nb1; j < b0 + nbk; ++j) anc[j].push_back(id);
-        build_rec(b0, nb1);
-        build_rec(b0 + nb1, nbk - nb1);
-        ends_at[b0 + nbk - 1].push_back(id);           // post-order: inner nodes are pushed first
-    }
+    // block-cyclic with alternating direction (0 1 .. G-1 | G-1 .. 1 0 | 0 1 ..): block column j receives j contributions, so a
+    // plain cyclic map gives the last rank ~15 % more update work than the first at 8 blocks per rank; the snake evens it out,
+    // and at every turn the owner of block column b also owns b + 1 (no hand-over on the critical path there)
+    // Ownership goes in pairs of block columns (kSuper): the owner of an even block column also owns the next one, whose
+    // critical-path hand-over then needs no broadcast at all (the panel is read where it was factored).
+    static constexpr int kSuper = 2;
+    int owner(int b) const { const int sb = b / kSuper, c = sb / world, p = sb % world; return (c & 1) ? world - 1 - p : p; }
     void build(int64_t n_, int64_t nb_, int world_) {
         n = n_; nb = nb_; world = world_;
         nblk = (int)((n + nb - 1) / nb);
-        nodes.clear();
-        anc.assign(nblk, {});
-        ends_at.assign(nblk, {});
-        build_rec(0, nblk);
     }
 };
 
 enum MgTraceCode { MG_T_UPDATE = 1, MG_T_FACTOR = 2, MG_T_BCAST = 3, MG_T_SWAP_LEFT = 4 };
-
-// One launch-level operation of an update task.
-struct MgOp {
-    int kind;                 // 0 row interchange, 1 TRSM diagonal block, 2 GEMM piece
-    char *p0, *p1, *p2;       // swap: block;  trsm: L, B;  gemm: C, A, B
-    int64_t a, b, c;          // swap: ncols, k0, k1;  trsm: k, nrhs;  gemm: m, n, k
-    double est_us;
-};
 
 struct MgRank;
 
@@ -165,15 +148,12 @@ struct MgRank {
     std::vector<char> up_pending;
     cudaEvent_t ev_sent = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_final = nullptr, ev_chunk[2] = {nullptr, nullptr};
     rfb_opts opts = {};
-    // Bulk-update slicing (set per problem by rank_setup from the bulk / critical-path balance, env overrides):
-    //   kmax        inner columns per GEMM launch (0 = never split k).  Fixed per problem: it decides the summation order.
-    //   piece_tiles 128 x 128 output tiles per GEMM launch (0 = never split rows); sm_count - 8 = one wave beside the
-    //               communication kernel's CTAs.  Row splitting does not change any result.
-    int64_t kmax = 2048;
-    int64_t piece_tiles = 140;
-    int merge_blocks = 1, merge_env = -1;   // owned block columns one bulk task may cover (see MgSched::build_task)
-    int64_t kmax_env = -1, piece_tiles_env = -1;
-    double slice_us = 250.0;
+    // Bulk slicing: one slice = panel b's contribution to as many consecutive owned block columns as fit `slice_us` of estimated
+    // work (at least one, at most merge_max); wider slices make better GEMM shapes, shorter ones bound how long the critical
+    // path can wait behind bulk work already in flight (two slices).  Env: RFB_MG_SLICE_US, RFB_MG_MERGE.
+    int merge_max = 16;
+    double slice_us = 500.0, alert_us = 350.0;
+    bool slice_env = false;
     int status = RFB_OK;
     std::string error;
     int64_t bcast_bytes = 0;
@@ -195,7 +175,16 @@ struct MgRank {
         return code;
     }
     char *Aj(int64_t r, int64_t lc) const { return A + ((size_t)r + (size_t)lc * (size_t)plan.n) * es; }
-    char *Lp(int64_t r, int64_t c) const { return L + ((size_t)r + (size_t)c * (size_t)plan.n) * es; }
+    // received panels: a ring of kRing slots, each n x nb with leading dimension n (the kernels share one lda with A);
+    // panel b sits in slot b % kRing, element (row r, column c of the panel) at Pn(b, r, c)
+    static constexpr int kRing = 6;
+    char *Pn(int b, int64_t r, int64_t c) const {
+        return L + ((size_t)(b % kRing) * (size_t)plan.n * (size_t)plan.nb + (size_t)r + (size_t)c * (size_t)plan.n) * es;
+    }
+    cudaEvent_t ev_slot[kRing] = {};
+    // critical-path timing of the last factorization (timing events around each owned block column's update + factorization,
+    // and around its publication): where the per-block-column chain time goes
+    std::vector<cudaEvent_t> tev_c0, tev_c1, tev_p0, tev_p1;
     void rec(int code, int64_t a, int64_t b, int64_t c, int64_t d) {
         trace->push_back(code); trace->push_back(a); trace->push_back(b); trace->push_back(c); trace->push_back(d);
     }
@@ -222,97 +211,39 @@ struct MgRank {
         }                                                                                     \
     } while (0)
 
-// ---- expansion of one update task U(node -> block j) into launch-level operations ----------------------------------------
-template <typename T>
-void emit_gemm(std::vector<MgOp> &ops, char *C, char *A, char *B, int64_t m, int64_t nn, int64_t k, int64_t lda, bool split,
-               int64_t kmax, int64_t piece_tiles) {
-    if (m <= 0 || nn <= 0 || k <= 0) return;
-    const int64_t kstep = kmax > 0 ? kmax : k;        // (not conditional on `split`: the k cut decides the summation order)
-    const int64_t tiles_n = (nn + 127) / 128;
-    const int64_t rstep = (split && piece_tiles > 0) ? 128 * std::max<int64_t>(1, piece_tiles / tiles_n) : m;
-    for (int64_t k0 = 0; k0 < k; k0 += kstep) {
-        const int64_t kk = std::min(kstep, k - k0);
-        for (int64_t r0 = 0; r0 < m; r0 += rstep) {
-            const int64_t mr = std::min(rstep, m - r0);
-            MgOp o{};
-            o.kind = 2;
-            o.p0 = C + (size_t)r0 * sizeof(T);
-            o.p1 = A + ((size_t)r0 + (size_t)k0 * (size_t)lda) * sizeof(T);
-            o.p2 = B + (size_t)k0 * sizeof(T);
-            o.a = mr; o.b = nn; o.c = kk;
-            o.est_us = 4.0 + 2.0 * (double)mr * (double)nn * (double)kk / (sizeof(T) == 8 ? 26e6 : 60e6);
-            ops.push_back(o);
-        }
-    }
-}
-
-template <typename T>
-void emit_trsm(std::vector<MgOp> &ops, char *Lm, int64_t k, char *B, int64_t nrhs, int64_t lda, bool split, int64_t kmax,
-               int64_t piece_tiles) {
-    constexpr int64_t tb = 256;                              // the fused 256-row block solve (trsm.cu)
-    if (k <= tb) {
-        MgOp o{};
-        o.kind = 1; o.p0 = Lm; o.p1 = B; o.a = k; o.b = nrhs;
-        o.est_us = 8.0 + (double)k * 0.14 * (double)((nrhs + 4735) / 4736);
-        ops.push_back(o);
-        return;
-    }
-    int64_t k1 = ((k / 2 + tb - 1) / tb) * tb;               // same split rule as trsm_rec
-    if (k1 >= k) k1 = ((k - 1) / tb) * tb;
-    emit_trsm<T>(ops, Lm, k1, B, nrhs, lda, split, kmax, piece_tiles);
-    emit_gemm<T>(ops, B + (size_t)k1 * sizeof(T), Lm + (size_t)k1 * sizeof(T), B, k - k1, nrhs, k1, lda, split, kmax, piece_tiles);
-    emit_trsm<T>(ops, Lm + ((size_t)k1 + (size_t)k1 * (size_t)lda) * sizeof(T), k - k1, B + (size_t)k1 * sizeof(T), nrhs, lda, split, kmax,
-                 piece_tiles);
-}
-
-template <typename T>
-int run_op(MgRank *r, const MgOp &o) {
-    rfb_ctx *ctx = r->ctx;
-    const int64_t lda = r->plan.n;
-    switch (o.kind) {
-        case 0: return rfb_launch_laswp_lists<T>(ctx, reinterpret_cast<T *>(o.p0), o.a, lda, o.b, o.c, r->plan.n);
-        case 1: return rfb_launch_trsm<T>(ctx, reinterpret_cast<const T *>(o.p0), o.a, reinterpret_cast<T *>(o.p1), o.b, lda, &r->opts);
-        default: return rfb_launch_gemm<T>(ctx, reinterpret_cast<T *>(o.p0), reinterpret_cast<const T *>(o.p1),
-                                           reinterpret_cast<const T *>(o.p2), o.a, o.b, o.c, lda, &r->opts);
-    }
-}
-
 // ---- the per-rank scheduler -----------------------------------------------------------------------------------------------
 template <typename T>
 struct MgSched {
     MgRank *r;
     const MgPlan &P;
-    int comm_cursor = 0;                       // next block whose publish (+ node-end swaps) goes onto the replica stream
-    std::vector<char> factored;                // own blocks: factorization enqueued
-    std::vector<int> next_task;                // own blocks: index into anc[j] of the next update task
-    std::vector<std::vector<MgOp>> ops;        // own blocks: operations of the task in progress
-    std::vector<size_t> op_pos;
+    int comm_cursor = 0;                 // next block whose publish goes onto the communication stream
+    std::vector<char> factored;          // own blocks: factorization enqueued
+    std::vector<int> next_src;           // own blocks: next source block whose contribution is still to be applied (== j: ready to factor)
+    std::vector<int> users_left;         // per source block: own blocks to its right that have not taken its contribution yet
     std::vector<char> touched;
-    // A bulk task may cover SEVERAL consecutive owned block columns that wait for the same node's update (they are adjacent in
-    // the rank's compact storage): one swap / TRSM / GEMM sequence with nrhs = the sum of their widths instead of one latency
-    // chain of diagonal blocks per 512 columns.  gcount[leader] = blocks in the task in progress, follower_of[j] = its leader.
-    std::vector<int> gcount, follower_of;
+    int last_arrived = -1;               // highest block column whose panel is known to have arrived
+    int next_left = 0;                   // next source block whose pivots go to the rank's finished columns on the left (:246)
     int chunks = 0;
 
     explicit MgSched(MgRank *rank) : r(rank), P(rank->plan) {
         factored.assign(P.nblk, 0);
-        next_task.assign(P.nblk, 0);
-        ops.assign(P.nblk, {});
-        op_pos.assign(P.nblk, 0);
+        next_src.assign(P.nblk, 0);
+        users_left.assign(P.nblk, 0);
         touched.assign(P.nblk, 0);
-        gcount.assign(P.nblk, 1);
-        follower_of.assign(P.nblk, -1);
+        for (int b = 0; b < P.nblk; ++b)
+            for (int j : r->own)
+                if (j > b) users_left[b]++;
     }
 
-    int dep_block(int node) const { return P.nodes[node].b0 + P.nodes[node].nb1 - 1; }   // last block of the node's left half
     bool recorded(int blk) const { return comm_cursor > blk; }
     bool arrived(int blk) const {
         if (!recorded(blk)) return false;
         if (r->dry) return true;
         return cudaEventQuery(r->ev_blk[blk]) == cudaSuccess;
     }
+    bool slot_is_free(int b) const { return b < 0 || users_left[b] == 0; }   // every user of panel b is at least enqueued
 
-    // ---- replica stream -----------------------------------------------------------------------------------------------
+    // ---- communication stream -----------------------------------------------------------------------------------------
     int publish(int b) {
         const int root = P.owner(b);
         const int64_t c0 = P.col0(b), w = P.width(b), rows = P.n - c0;
@@ -322,8 +253,12 @@ struct MgSched {
         const size_t off_piv = pbytes, off_dst = pbytes + 8 * (size_t)w, off_src = pbytes + 16 * (size_t)w, off_w = pbytes + 24 * (size_t)w;
         const size_t total = pbytes + 28 * (size_t)w;
         cudaStream_t s = r->s_L;
+        // the ring slot of panel b held panel b - kRing: its last reader on the compute stream must be done
+        if (b >= MgRank::kRing && !r->own.empty() && r->own.back() > b - MgRank::kRing)
+            MG_CUDA(r, cudaStreamWaitEvent(s, r->ev_slot[b % MgRank::kRing], 0));
         if (r->rank == root) {
             MG_CUDA(r, cudaStreamWaitEvent(s, r->ev_fact[b], 0));
+            MG_CUDA(r, cudaEventRecord(r->tev_p0[b], s));
             if (P.world > 1) {
                 MG_CUDA(r, cudaMemcpy2DAsync(r->stage, rows * es, r->Aj(c0, r->lcol[b]), P.n * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
                 MG_CUDA(r, cudaMemcpyAsync(r->stage + off_piv, r->ipiv + c0, 8 * w, cudaMemcpyDeviceToDevice, s));
@@ -335,11 +270,13 @@ struct MgSched {
         if (P.world > 1) {
             MG_NCCL(r, nccl_api()->Broadcast(r->stage, r->stage, total, ncclUint8, root, r->comm, s));
             r->bcast_bytes += (int64_t)total;
-            if (r->rank == root) {       // the owner's next compute work must not take the SMs before its send has started
+            // the owner's next BULK work must not take the SMs before its send has gone out -- unless the owner also owns the next
+            // block column: then the critical path continues right here and must not wait for this broadcast
+            if (r->rank == root && !(b + 1 < P.nblk && P.owner(b + 1) == r->rank)) {
                 MG_CUDA(r, cudaEventRecord(r->ev_sent, s));
                 MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_sent, 0));
             }
-            MG_CUDA(r, cudaMemcpy2DAsync(r->Lp(c0, c0), P.n * es, r->stage, rows * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
+            MG_CUDA(r, cudaMemcpy2DAsync(r->Pn(b, c0, 0), P.n * es, r->stage, rows * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
             if (r->rank != root) {
                 MG_CUDA(r, cudaMemcpyAsync(r->ipiv + c0, r->stage + off_piv, 8 * w, cudaMemcpyDeviceToDevice, s));
                 MG_CUDA(r, cudaMemcpyAsync(r->pdst + 2 * c0, r->stage + off_dst, 8 * w, cudaMemcpyDeviceToDevice, s));
@@ -347,35 +284,8 @@ struct MgSched {
                 MG_CUDA(r, cudaMemcpyAsync(r->pwidth + c0, r->stage + off_w, 4 * w, cudaMemcpyDeviceToDevice, s));
             }
         } else {
-            MG_CUDA(r, cudaMemcpy2DAsync(r->Lp(c0, c0), P.n * es, r->Aj(c0, r->lcol[b]), P.n * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
+            MG_CUDA(r, cudaMemcpy2DAsync(r->Pn(b, c0, 0), P.n * es, r->Aj(c0, r->lcol[b]), P.n * es, rows * es, w, cudaMemcpyDeviceToDevice, s));
         }
-        return RFB_OK;
-    }
-
-    // src/lu.jl:246 for node `id`: pivots of its right half applied to its left half's columns (rows below the left half)
-    int swap_left(int id) {
-        const MgNode &N = P.nodes[id];
-        const int64_t c0 = P.col0(N.b0), n1 = (int64_t)N.nb1 * P.nb;
-        const int64_t k0 = c0 + n1, k1 = std::min<int64_t>(P.n, P.col0(N.b0 + N.nbk));
-        if (r->dry) { r->rec(MG_T_SWAP_LEFT, c0, n1, k0, k1); return RFB_OK; }
-        cudaStream_t s = r->s_L;
-        // every reader of this region on the compute stream precedes the factorization of this rank's last block of the node
-        int last_own = -1;
-        for (int j = N.b0 + N.nbk - 1; j >= N.b0; --j)
-            if (P.owner(j) == r->rank) { last_own = j; break; }
-        if (last_own >= 0) MG_CUDA(r, cudaStreamWaitEvent(s, r->ev_fact[last_own], 0));
-        rfb_ctx *ctx = r->ctx;
-        ctx->stream = s;
-        ctx->lane = 1;
-        int rc = rfb_launch_laswp_lists<T>(ctx, reinterpret_cast<T *>(r->Lp(k0, c0)), n1, P.n, k0, k1, P.n);
-        int first_own = -1, cnt = 0;
-        for (int j = N.b0; j < N.b0 + N.nb1; ++j)
-            if (P.owner(j) == r->rank) { if (first_own < 0) first_own = j; cnt++; }
-        if (rc == RFB_OK && cnt > 0)           // the rank's own copy of those columns (contiguous: local storage is in block order)
-            rc = rfb_launch_laswp_lists<T>(ctx, reinterpret_cast<T *>(r->Aj(k0, r->lcol[first_own])), (int64_t)cnt * P.nb, P.n, k0, k1, P.n);
-        ctx->stream = r->s_comp;
-        ctx->lane = 0;
-        MG_TRY(r, rc);
         return RFB_OK;
     }
 
@@ -383,71 +293,63 @@ struct MgSched {
         while (comm_cursor < P.nblk) {
             const int b = comm_cursor;
             if (P.owner(b) == r->rank && !factored[b]) break;
+            if (!r->dry && !slot_is_free(b - MgRank::kRing)) break;         // the ring is full: the compute side has to catch up first
             MG_TRY(r, publish(b));
-            for (int id : P.ends_at[b]) MG_TRY(r, swap_left(id));
             if (!r->dry) MG_CUDA(r, cudaEventRecord(r->ev_blk[b], r->s_L));
+            if (!r->dry && P.owner(b) == r->rank) MG_CUDA(r, cudaEventRecord(r->tev_p1[b], r->s_L));
             comm_cursor++;
         }
         return RFB_OK;
     }
 
     // ---- compute stream -----------------------------------------------------------------------------------------------
-    void build_task(int j, bool merge) {
-        const int id = P.anc[j][next_task[j]];
-        const MgNode &N = P.nodes[id];
-        const int64_t c0 = P.col0(N.b0), n1 = (int64_t)N.nb1 * P.nb, lc = r->lcol[j];
-        int64_t w = P.width(j);
-        gcount[j] = 1;
-        if (merge) {       // the following owned block columns whose next pending update is this same node
-            for (int j2 = j + P.world; j2 < P.nblk; j2 += P.world) {
-                if (gcount[j] >= r->merge_blocks) break;
-                if (next_task[j2] >= (int)P.anc[j2].size() || P.anc[j2][next_task[j2]] != id || !ops[j2].empty() || follower_of[j2] >= 0) break;
-                follower_of[j2] = j;
-                gcount[j]++;
-                w += P.width(j2);
-            }
-        }
-        const bool split = merge || next_task[j] + 1 < (int)P.anc[j].size();   // the lowest update alone runs on the critical path: whole launches
-        std::vector<MgOp> &v = ops[j];
-        v.clear();
-        op_pos[j] = 0;
-        MgOp s{};
-        s.kind = 0; s.p0 = r->Aj(c0, lc); s.a = w; s.b = c0; s.c = c0 + n1;
-        s.est_us = 6.0 + 32.0 * (double)n1 * (double)w / 2.5e6;
-        v.push_back(s);                                                                                  // :233
-        emit_trsm<T>(v, r->Lp(c0, c0), n1, r->Aj(c0, lc), w, P.n, split, r->kmax, r->piece_tiles);       // :235
-        emit_gemm<T>(v, r->Aj(c0 + n1, lc), r->Lp(c0 + n1, c0), r->Aj(c0, lc), P.n - c0 - n1, w, n1, P.n, split, r->kmax,
-                     r->piece_tiles);                                                                    // :240
-    }
-
-    // enqueue operations of block j's current task until `budget_us` of estimated work is out (or the task ends)
-    int advance_task(int j, double budget_us, bool merge) {
+    // panel b's step of reckernel! (src/lu.jl:233-240) on `cnt` consecutive owned block columns starting at block j
+    // `local`: read panel b where this rank factored it (its own storage) instead of from the ring, and do not wait for its
+    // publication -- only for the block column right after it, before any later pivots have touched those rows
+    int contribute(int b, size_t q, int cnt, bool local = false) {             // q: position of the first target in r->own
+        const int64_t c0 = P.col0(b), w = P.width(b);
+        const int j = r->own[q];
         if (r->dry) {
-            const MgNode &N = P.nodes[P.anc[j][next_task[j]]];
-            r->rec(MG_T_UPDATE, P.col0(N.b0), (int64_t)N.nb1 * P.nb, j, 0);
-            next_task[j]++;
+            for (int g = 0; g < cnt; ++g) { const int jj = r->own[q + g]; r->rec(MG_T_UPDATE, c0, w, jj, 1); next_src[jj] = b + 1; users_left[b]--; }
             return RFB_OK;
         }
-        if (ops[j].empty()) {
-            build_task(j, merge);
-            for (int g = 0, jj = j; g < gcount[j]; ++g, jj += P.world) {
-                if (touched[jj]) continue;
+        int64_t ncols = 0;
+        for (int g = 0; g < cnt; ++g) {
+            const int jj = r->own[q + g];
+            ncols += P.width(jj);
+            if (!touched[jj]) {
                 touched[jj] = 1;
                 if (r->up_pending[jj]) { MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_up[jj], 0)); r->up_pending[jj] = 0; }
             }
-            MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_blk[dep_block(P.anc[j][next_task[j]])], 0));
         }
-        double out = 0;
-        while (op_pos[j] < ops[j].size() && out < budget_us) {
-            const MgOp &o = ops[j][op_pos[j]++];
-            MG_TRY(r, run_op<T>(r, o));
-            out += o.est_us;
-        }
-        if (op_pos[j] >= ops[j].size()) {
-            ops[j].clear();
-            for (int g = 0, jj = j; g < gcount[j]; ++g, jj += P.world) { next_task[jj]++; follower_of[jj] = -1; }
-            gcount[j] = 1;
-        }
+        if (!local) MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_blk[b], 0));
+        rfb_ctx *ctx = r->ctx;
+        T *Ablk = reinterpret_cast<T *>(r->Aj(c0, r->lcol[j]));                 // rows c0.. of the target columns
+        const T *Lb = reinterpret_cast<const T *>(local ? r->Aj(c0, r->lcol[b]) : r->Pn(b, c0, 0));   // panel b, rows c0..
+        ctx->lane = 2 + b % MgRank::kRing;                  // block column b's composed interchanges: built once, used by every slice
+        const int rc_swap = rfb_launch_laswp_lists<T>(ctx, Ablk, ncols, P.n, c0, c0 + w, P.n, b);                       // :233
+        ctx->lane = 0;
+        MG_TRY(r, rc_swap);
+        MG_TRY(r, rfb_launch_trsm<T>(ctx, Lb, w, Ablk, ncols, P.n, &r->opts));                                         // :235
+        MG_TRY(r, rfb_launch_gemm<T>(ctx, Ablk + w, Lb + w, Ablk, P.n - c0 - w, ncols, w, P.n, &r->opts));              // :240
+        for (int g = 0; g < cnt; ++g) { next_src[r->own[q + g]] = b + 1; users_left[b]--; }
+        if (users_left[b] == 0) MG_CUDA(r, cudaEventRecord(r->ev_slot[b % MgRank::kRing], r->s_comp));   // the slot may be overwritten
+        return RFB_OK;
+    }
+
+    // src/lu.jl:246 for source block b: its pivots applied to the rank's finished columns on its left (rows below b's diagonal)
+    int swap_left(int b) {
+        const int64_t c0 = P.col0(b), w = P.width(b);
+        if (r->dry) { r->rec(MG_T_SWAP_LEFT, 0, c0, c0, c0 + w); return RFB_OK; }
+        int64_t ncols = 0;
+        for (int j : r->own)
+            if (j < b) ncols += P.width(j);
+        if (ncols == 0) return RFB_OK;
+        MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_blk[b], 0));
+        r->ctx->lane = 2 + b % MgRank::kRing;
+        const int rc_swap = rfb_launch_laswp_lists<T>(r->ctx, reinterpret_cast<T *>(r->Aj(c0, 0)), ncols, P.n, c0, c0 + w, P.n, b);
+        r->ctx->lane = 0;
+        MG_TRY(r, rc_swap);
         return RFB_OK;
     }
 
@@ -466,7 +368,15 @@ struct MgSched {
         else rc = rfb_lu_range_f32(r->ctx, reinterpret_cast<float *>(root), P.n, P.n, c0, w, r->ipiv, r->info, &r->opts);
         MG_TRY(r, rc);
         MG_CUDA(r, cudaEventRecord(r->ev_fact[j], r->s_comp));
+        MG_CUDA(r, cudaEventRecord(r->tev_c1[j], r->s_comp));
         return RFB_OK;
+    }
+
+    // estimated device time (us) of panel b's contribution to ncols columns
+    double est_us(int b, int64_t ncols) const {
+        const double w = (double)P.width(b), below = (double)(P.n - P.col0(b)) - w;
+        const double rate = sizeof(T) == 8 ? 26e6 : 60e6;                        // flops per microsecond
+        return 60.0 + 2.0 * below * (double)ncols * w / rate + w * w * (double)ncols / rate;
     }
 
     int chunks_in_flight() {
@@ -485,44 +395,77 @@ struct MgSched {
         size_t own_pos = 0;                                          // index into r->own of the next block to factor
         auto idle_since = clock::now();
         bool idling = false;
+        auto progress = [&] {
+            if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
+            last_progress = clock::now();
+        };
         while (true) {
             MG_TRY(r, advance_comm());
             while (own_pos < r->own.size() && factored[r->own[own_pos]]) own_pos++;
-            if (own_pos >= r->own.size()) {
-                if (comm_cursor >= P.nblk) break;
-                continue;                                             // only other ranks' blocks remain: advance_comm enqueues them all
+            const bool own_done = own_pos >= r->own.size();
+            if (own_done && comm_cursor >= P.nblk && next_left >= P.nblk) break;
+            // 1. critical path: the next owned block column only waits for contributions whose panels have all arrived
+            if (!own_done) {
+                const int jn = r->own[own_pos];
+                // ready when panel jn - 1 has arrived -- or was factored right here (then nothing older can be missing either)
+                // (every older panel must at least be ON ITS WAY into the ring -- recorded -- for the stream waits to mean anything:
+                //  with a full ring the communication cursor can lag behind this rank's own factorizations)
+                const bool pred_local = jn > 0 && P.owner(jn - 1) == r->rank && factored[jn - 1] && (jn < 2 || recorded(jn - 2));
+                if (jn == 0 || pred_local || arrived(jn - 1)) {
+                    progress();
+                    if (!r->dry) MG_CUDA(r, cudaEventRecord(r->tev_c0[jn], r->s_comp));
+                    while (next_src[jn] < jn) {
+                        const int b = next_src[jn];
+                        MG_TRY(r, contribute(b, own_pos, 1, pred_local && b == jn - 1 && !arrived(b)));
+                    }
+                    MG_TRY(r, factor(jn));
+                    r->st_crit++;
+                    continue;
+                }
             }
-            const int jn = r->own[own_pos];
-            // critical path: everything block jn still waits for has arrived -> its remaining updates and its factorization, back to back
-            bool crit = true;
-            for (int t = next_task[jn]; t < (int)P.anc[jn].size() && crit; ++t) crit = arrived(dep_block(P.anc[jn][t]));
-            if (crit) {
-                if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
-                while (next_task[jn] < (int)P.anc[jn].size()) MG_TRY(r, advance_task(jn, 1e30, false));
-                MG_TRY(r, factor(jn));
-                r->st_crit++;
-                last_progress = clock::now();
-                continue;
+            // how far the critical path is from this rank: d panels still have to arrive before its next block column is ready.
+            // d >= 2: at least one whole block column is factored elsewhere first -> wide slices, two in flight;
+            // d == 1: the next arrival makes this rank critical -> short slices, one in flight (it must react at once)
+            while (last_arrived + 1 < P.nblk && arrived(last_arrived + 1)) last_arrived++;
+            const int dist = own_done ? 1 << 20 : r->own[own_pos] - 1 - last_arrived;
+            const bool alert = dist <= 1 && !own_done;
+            const double slice_target = alert ? std::min(r->slice_us, r->alert_us) : r->slice_us;
+            const bool room = r->dry || chunks_in_flight() < (alert ? 1 : 2);
+            // 2. bulk: the oldest pending contribution to the owned block columns nearest to the critical path
+            bool did = false;
+            if (room) {
+                for (size_t q = own_pos; q < r->own.size() && !did; ++q) {
+                    const int j = r->own[q], b = next_src[j];
+                    if (b >= j || !arrived(b)) continue;
+                    int cnt = 1;
+                    int64_t ncols = P.width(j);
+                    for (size_t q2 = q + 1; q2 < r->own.size() && cnt < r->merge_max; ++q2) {
+                        const int j2 = r->own[q2];
+                        if (next_src[j2] != b || est_us(b, ncols + P.width(j2)) > slice_target) break;
+                        ncols += P.width(j2);
+                        cnt++;
+                    }
+                    progress();
+                    MG_TRY(r, contribute(b, q, cnt));
+                    did = true;
+                }
+                // 3. the pivots of arrived panels, in order, to the finished columns on their left
+                if (!did && next_left < P.nblk && arrived(next_left)) {
+                    progress();
+                    MG_TRY(r, swap_left(next_left));
+                    next_left++;
+                    did = true;
+                }
+                if (did) {
+                    if (!r->dry) { MG_CUDA(r, cudaEventRecord(r->ev_chunk[chunks & 1], r->s_comp)); chunks++; }
+                    r->st_slices++;
+                    continue;
+                }
             }
-            // otherwise one bounded slice of the most urgent update whose inputs have arrived (at most two slices in flight)
-            int pick = -1;
-            for (size_t q = own_pos; q < r->own.size(); ++q) {
-                const int j = r->own[q];
-                if (follower_of[j] >= 0) continue;                 // rides in a merged task led by an earlier block column
-                if (next_task[j] < (int)P.anc[j].size() && arrived(dep_block(P.anc[j][next_task[j]]))) { pick = j; break; }
-            }
-            if (pick >= 0 && (r->dry || chunks_in_flight() < 2)) {
-                if (idling) { r->st_idle_us += std::chrono::duration<double, std::micro>(clock::now() - idle_since).count(); idling = false; }
-                MG_TRY(r, advance_task(pick, r->slice_us, true));
-                if (!r->dry) { MG_CUDA(r, cudaEventRecord(r->ev_chunk[chunks & 1], r->s_comp)); chunks++; }
-                r->st_slices++;
-                last_progress = clock::now();
-                continue;
-            }
-            if (pick < 0 && !idling && !r->dry && chunks_in_flight() == 0) { idling = true; idle_since = clock::now(); }   // nothing to run at all
-            if (r->dry) return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule cannot make progress (block %d)", jn);
+            if (r->dry) return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule cannot make progress (rank %d, cursor %d)", r->rank, comm_cursor);
+            if (room && !idling && chunks_in_flight() == 0) { idling = true; idle_since = clock::now(); }   // nothing runnable at all
             if (std::chrono::duration<double>(clock::now() - last_progress).count() > 60.0)
-                return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule stalled for 60 s waiting for block %d (rank %d)", jn, r->rank);
+                return r->fail(RFB_ERR_INTERNAL, "multi-GPU schedule stalled for 60 s (rank %d, communication cursor %d)", r->rank, comm_cursor);
             std::this_thread::yield();
         }
         r->st_wall_us = std::chrono::duration<double, std::micro>(clock::now() - t_begin).count();
@@ -540,7 +483,7 @@ int rank_free_problem(MgRank *r) {
     r->A = r->L = r->stage = nullptr;
     r->ipiv = r->info = nullptr;
     r->pdst = r->psrc = r->pwidth = nullptr;
-    for (auto *v : {&r->ev_blk, &r->ev_fact, &r->ev_up}) {
+    for (auto *v : {&r->ev_blk, &r->ev_fact, &r->ev_up, &r->tev_c0, &r->tev_c1, &r->tev_p0, &r->tev_p1}) {
         for (cudaEvent_t e : *v) if (e) cudaEventDestroy(e);
         v->clear();
     }
@@ -557,20 +500,14 @@ int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
     r->f32 = f32;
     r->es = f32 ? 4 : 8;
     {
-        // balance of this problem on this many ranks: bulk = all GEMM-shaped work of one rank at a typical rate, critical path =
-        // every block column's pivot chain (one all-CTA exchange per column) + its in-block updates, broadcast and hand-over
+        // Balance of this problem on this many ranks: bulk = one rank's share of the GEMM-shaped work at a typical rate; critical
+        // path = every block column's pivot chain (one all-CTA exchange per column) + its in-block updates + the hand-over.  The
+        // more bulk-bound, the wider the slices (better GEMM shapes, fixed per-slice costs amortised); the more
+        // critical-path-bound, the shorter (the critical path waits for at most two slices in flight).
         const double t_bulk = (2.0 / 3.0) * (double)n * (double)n * (double)n / r->world / (f32 ? 60e12 : 28e12);
         const double t_crit = (double)r->plan.nblk * ((double)nb * 2.4e-6 + 1.2e-3);
         const double ratio = t_bulk / t_crit;
-        const int64_t wave = std::max(32, r->ctx->sm_count - 8);
-        if (ratio > 0.8) { r->kmax = 4096; r->piece_tiles = 2 * wave; }       // bulk-bound: two-wave pieces (~1 ms), the pivot chain has slack
-        else { r->kmax = 2048; r->piece_tiles = wave; }                        // critical-path-bound: one-wave pieces, <= 0.3 ms each
-        // merging amortises the per-task latency chain (n1 / 256 dependent diagonal blocks + as many small GEMMs, ~4 ms at the
-        // root) over more columns, but the first block column of a merged task is only ready when the whole task is
-        r->merge_blocks = ratio > 2.0 ? 4 : (ratio > 0.8 ? 2 : 1);
-        if (r->merge_env > 0) r->merge_blocks = r->merge_env;
-        if (r->kmax_env >= 0) r->kmax = r->kmax_env;
-        if (r->piece_tiles_env >= 0) r->piece_tiles = r->piece_tiles_env;
+        if (!r->slice_env) r->slice_us = ratio > 2.0 ? 3000.0 : 1300.0;
     }
     r->opts = rfb_opts{};
     r->opts.mem_space = RFB_MEM_DEVICE;
@@ -583,14 +520,16 @@ int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
         if (P.owner(j) == r->rank) { r->own.push_back(j); r->lcol[j] = r->ncl; r->ncl += P.width(j); }
     const size_t nn = (size_t)n;
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
-    bool ok = alloc((void **)&r->L, nn * nn * r->es) && alloc((void **)&r->A, nn * (size_t)std::max<int64_t>(r->ncl, 1) * r->es) &&
+    bool ok = alloc((void **)&r->L, (size_t)MgRank::kRing * nn * (size_t)nb * r->es) &&
+              alloc((void **)&r->A, nn * (size_t)std::max<int64_t>(r->ncl, 1) * r->es) &&
               alloc((void **)&r->stage, nn * (size_t)nb * r->es + 28 * (size_t)nb + 256) && alloc((void **)&r->ipiv, 8 * (nn + 64)) &&
               alloc((void **)&r->info, 64) && alloc((void **)&r->pdst, 4 * (2 * nn + 128)) && alloc((void **)&r->psrc, 4 * (2 * nn + 128)) &&
               alloc((void **)&r->pwidth, 4 * (nn + 64));
     if (!ok) {
         cudaGetLastError();
         rank_free_problem(r);
-        return r->fail(RFB_ERR_NOMEM, "rank %d: cannot allocate the replica (%zu bytes) and the own block columns", r->rank, nn * nn * r->es);
+        return r->fail(RFB_ERR_NOMEM, "rank %d: cannot allocate the own block columns (%zu bytes) and the panel ring", r->rank,
+                       nn * (size_t)std::max<int64_t>(r->ncl, 1) * r->es);
     }
     r->ctx->perm_dst = r->pdst; r->ctx->perm_src = r->psrc; r->ctx->perm_width = r->pwidth;
     r->ctx->perm_cap = nn + 64;
@@ -598,12 +537,16 @@ int rank_setup(MgRank *r, int64_t n, int64_t nb, bool f32) {
     r->ev_blk.assign(P.nblk, nullptr);
     r->ev_fact.assign(P.nblk, nullptr);
     r->ev_up.assign(P.nblk, nullptr);
+    r->tev_c0.assign(P.nblk, nullptr); r->tev_c1.assign(P.nblk, nullptr);
+    r->tev_p0.assign(P.nblk, nullptr); r->tev_p1.assign(P.nblk, nullptr);
     r->up_pending.assign(P.nblk, 0);
     for (int j = 0; j < P.nblk; ++j) {
         MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_blk[j], cudaEventDisableTiming));
         if (P.owner(j) == r->rank) {
             MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_fact[j], cudaEventDisableTiming));
             MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_up[j], cudaEventDisableTiming));
+            MG_CUDA(r, cudaEventCreate(&r->tev_c0[j])); MG_CUDA(r, cudaEventCreate(&r->tev_c1[j]));
+            MG_CUDA(r, cudaEventCreate(&r->tev_p0[j])); MG_CUDA(r, cudaEventCreate(&r->tev_p1[j]));
         }
     }
     MG_CUDA(r, cudaMemset(r->info, 0, 64));
@@ -625,12 +568,12 @@ int rank_create(MgRank *r) {
     MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_final, cudaEventDisableTiming));
     MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_chunk[0], cudaEventDisableTiming));
     MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_chunk[1], cudaEventDisableTiming));
+    for (int i = 0; i < MgRank::kRing; ++i) MG_CUDA(r, cudaEventCreateWithFlags(&r->ev_slot[i], cudaEventDisableTiming));
     MG_CUDA(r, cudaEventCreate(&r->ev_t0));
     MG_CUDA(r, cudaEventCreate(&r->ev_t1));
-    if (const char *e = getenv("RFB_MG_KMAX")) r->kmax_env = atoll(e);
-    if (const char *e = getenv("RFB_MG_PIECE_TILES")) r->piece_tiles_env = atoll(e);
-    if (const char *e = getenv("RFB_MG_MERGE")) r->merge_env = atoi(e);
-    if (const char *e = getenv("RFB_MG_SLICE_US")) r->slice_us = atof(e);
+    if (const char *e = getenv("RFB_MG_MERGE")) r->merge_max = std::max(1, atoi(e));
+    if (const char *e = getenv("RFB_MG_SLICE_US")) { r->slice_us = atof(e); r->slice_env = true; }
+    if (const char *e = getenv("RFB_MG_ALERT_US")) r->alert_us = atof(e);
     return RFB_OK;
 }
 
@@ -642,7 +585,7 @@ int rank_comm_init(MgRank *r, const ncclUniqueId &id) {
         ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
         // the broadcast kernel waits for the owner while GEMM waves run beside it: keep its footprint to a few SMs
         const char *e = getenv("RFB_MG_NCCL_MAX_CTAS");
-        cfg.maxCTAs = e ? atoi(e) : 8;
+        cfg.maxCTAs = e ? atoi(e) : 16;     // measured on 8 GPUs: 16 -> 188 ms, 8 -> 195 ms per 32768^2 factorization
         cfg.minCTAs = 1;
         MG_NCCL(r, api->CommInitRankConfig(&r->comm, r->world, id, r->rank, &cfg));
     } else {
@@ -659,6 +602,7 @@ void rank_destroy(MgRank *r) {
         if (r->comm) nccl_api()->CommDestroy(r->comm);
         for (cudaEvent_t e : {r->ev_sent, r->ev_final, r->ev_chunk[0], r->ev_chunk[1], r->ev_t0, r->ev_t1})
             if (e) cudaEventDestroy(e);
+        for (int i = 0; i < MgRank::kRing; ++i) if (r->ev_slot[i]) cudaEventDestroy(r->ev_slot[i]);
         if (r->s_L) cudaStreamDestroy(r->s_L);
         if (r->s_copy) cudaStreamDestroy(r->s_copy);
         rfb_destroy(r->ctx);
@@ -674,6 +618,7 @@ int rank_factor(MgRank *r) {
     r->status = RFB_OK;
     r->ctx->stream = r->s_comp;
     r->ctx->lane = 0;
+    for (int i = 0; i < rfb_ctx::kLanes; ++i) r->ctx->net_key[i] = -1;
     MG_CUDA(r, cudaEventRecord(r->ev_t0, r->s_comp));
     MG_CUDA(r, cudaMemsetAsync(r->info, 0, 64, r->s_comp));
     MG_CUDA(r, cudaMemsetAsync(r->pdst, 0xFF, 4 * (2 * (size_t)P.n + 128), r->s_comp));
@@ -688,9 +633,11 @@ int rank_factor(MgRank *r) {
         if (r->comm && r->world > 1) nccl_api()->CommAbort(r->comm), r->comm = nullptr;     // never leave a collective hanging on the device
         return rc;
     }
-    MG_CUDA(r, cudaEventRecord(r->ev_final, r->s_L));
-    MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_final, 0));
+    // the factorization is complete when BOTH streams are: the compute stream joins the communication stream, then closes the timer
+    MG_CUDA(r, cudaEventRecord(r->ev_sent, r->s_L));
+    MG_CUDA(r, cudaStreamWaitEvent(r->s_comp, r->ev_sent, 0));
     MG_CUDA(r, cudaEventRecord(r->ev_t1, r->s_comp));
+    MG_CUDA(r, cudaEventRecord(r->ev_final, r->s_comp));
     return RFB_OK;
 }
 
@@ -860,6 +807,13 @@ int rfb_mg_setup(rfb_mg *mg, int64_t n, int64_t nb, int is_f32) {
     return for_ranks(mg, [&](MgRank *r) { rank_setup(r, n, nb, is_f32 != 0); });
 }
 
+int rfb_mg_owner_of(int64_t block, int world) {
+    if (block < 0 || world < 1) return -1;
+    MgPlan p;
+    p.world = world;
+    return p.owner((int)block);
+}
+
 int rfb_mg_local_ranks(rfb_mg *mg, int *count, int *world) {
     if (!mg) return RFB_ERR_ARG;
     if (count) *count = (int)mg->ranks.size();
@@ -984,6 +938,20 @@ int rfb_mg_sched_stats(rfb_mg *mg, int lr, int64_t out[8]) {
     for (int i = 0; i < 8; ++i) out[i] = 0;
     out[0] = r->st_slices; out[1] = r->st_crit; out[2] = (int64_t)r->st_idle_us; out[3] = (int64_t)r->st_wall_us;
     out[4] = r->ctx ? r->ctx->launches : 0;
+    // [5] device microseconds spent in the owned block columns' critical sections (last contributions + factorization),
+    // [6] device microseconds from "factored" to "published here" (pack + broadcast + unpack) of the owned block columns
+    if (r->ctx && !r->tev_c0.empty()) {
+        cudaSetDevice(r->device);
+        double crit = 0, pub = 0;
+        for (int j : r->own) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, r->tev_c0[j], r->tev_c1[j]) == cudaSuccess) crit += t;
+            if (cudaEventElapsedTime(&t, r->tev_p0[j], r->tev_p1[j]) == cudaSuccess) pub += t;
+        }
+        cudaGetLastError();
+        out[5] = (int64_t)(crit * 1e3);
+        out[6] = (int64_t)(pub * 1e3);
+    }
     return RFB_OK;
 }
 

@@ -26,7 +26,9 @@ from . import _lib
 # host logic mirrored from the C++ plan (ownership only; the schedule itself is `rfb_mg_trace`)
 # ----------------------------------------------------------------------------------------------
 def owner_of(block: int, world: int) -> int:
-    return block % world
+    """Rank that owns block column `block`: pairs of block columns dealt out cyclically with alternating direction
+    (`rfb_mg_owner_of`, the one definition: MgPlan::owner in csrc/rfb_mg.cu)."""
+    return int(_lib.load().rfb_mg_owner_of(block, world))
 
 
 def block_range(j: int, n: int, nb: int) -> Tuple[int, int]:
@@ -88,7 +90,8 @@ class _MgHandle:
     def sched_stats(self, lr: int = 0) -> dict:
         out = (C.c_int64 * 8)()
         self._check(self._lib.rfb_mg_sched_stats(self._h, lr, out))
-        return {"bulk_slices": out[0], "critical_enqueues": out[1], "host_idle_ms": out[2] / 1e3, "schedule_loop_ms": out[3] / 1e3}
+        return {"bulk_slices": out[0], "critical_enqueues": out[1], "host_idle_ms": out[2] / 1e3, "schedule_loop_ms": out[3] / 1e3,
+                "critical_sections_device_ms": out[5] / 1e3, "publications_device_ms": out[6] / 1e3}
 
     def stats(self) -> dict:
         b, l = C.c_int64(), C.c_int64()

@@ -25,8 +25,9 @@ class NumpyBackend:
         self.O = O
         self.n, self.nb, self.rank, self.world = a_full.shape[0], nb, rank, world
         self.A = np.zeros_like(a_full, order="F")          # only own block columns are filled in
+        from rfb200.dist_lu import owner_of
         for j in range((self.n + nb - 1) // nb):
-            if j % world == rank:
+            if owner_of(j, world) == rank:
                 self.A[:, j * nb:(j + 1) * nb] = a_full[:, j * nb:(j + 1) * nb]
         self.ipiv = np.zeros(self.n, dtype=np.int64)
         self.info = 0
@@ -59,7 +60,7 @@ class NumpyBackend:
 
     def update(self, blocks, c0, n1):
         import scipy.linalg as sl
-        assert all(b % self.world == self.rank for b in blocks) and blocks == sorted(blocks)
+        assert blocks == sorted(blocks)
         for j in blocks:
             col0 = j * self.nb
             ncols = min(self.n, col0 + self.nb) - col0
@@ -145,36 +146,39 @@ def test_ownership_helpers():
     sys.path.insert(0, ROOT)
     import rfb200
     from rfb200.dist_lu import block_range, owned_blocks, owner_of
-    assert [owner_of(j, 8) for j in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
-    assert owned_blocks(1, 4, 1000, 128) == [1, 5]
+    assert [owner_of(j, 4) for j in range(18)] == [0, 0, 1, 1, 2, 2, 3, 3, 3, 3, 2, 2, 1, 1, 0, 0, 0, 0]
+    assert owned_blocks(1, 4, 1000, 128) == [2, 3]
+    for world in (1, 2, 3, 8):
+        counts = [len(owned_blocks(r, world, 64 * 512, 512)) for r in range(world)]
+        assert max(counts) - min(counts) <= 2 and sum(counts) == 64
     assert block_range(7, 1000, 128) == (896, 104)
     assert sum(block_range(j, 1000, 128)[1] for j in range(8)) == 1000
 
 
-def test_trace_is_left_looking_per_block_and_complete():
-    """Structure of the C++ schedule: every block column is broadcast exactly once and in block order on every rank,
-    an owned block column receives one update per ancestor whose right half holds it (top-down, the lowest last),
-    then is factored, then published; A21 <- P2 A21 (src/lu.jl:246) appears once per internal node on every rank."""
+def test_trace_structure():
+    """Structure of the C++ schedule (rfb_mg_trace): every block column is broadcast exactly once and in block order on
+    every rank; an owned block column receives the contribution of EVERY block column on its left, in order (the last one
+    right before it is factored -- the look-ahead step), then is factored, then published; the pivots of every block
+    column are applied once to the rank's finished columns on the left (src/lu.jl:246)."""
     sys.path.insert(0, ROOT)
     import rfb200  # noqa: F401
     from rfb200.dist_lu import TRACE_BCAST, TRACE_FACTOR, TRACE_SWAP_LEFT, TRACE_UPDATE, trace_schedule
-    n, nb, world = 64 * 13, 64, 4
+    n, nb, world = 64 * 13 - 20, 64, 4
     nblk = 13
-    swaps = None
     for rank in range(world):
         t = trace_schedule(n, nb, rank, world).tolist()
         assert [op[1] for op in t if op[0] == TRACE_BCAST] == list(range(nblk))
-        mine = [j for j in range(nblk) if j % world == rank]
+        from rfb200.dist_lu import owner_of
+        mine = [j for j in range(nblk) if owner_of(j, world) == rank]
         assert [op[1] for op in t if op[0] == TRACE_FACTOR] == mine
         for j in mine:
-            ups = [(op[1], op[2]) for op in t if op[0] == TRACE_UPDATE and op[3] == j]
-            assert all(c0 + n1 <= j * nb for c0, n1 in ups)                       # the left half ends before block j
-            assert [u[1] for u in ups] == sorted((u[1] for u in ups), reverse=True)   # top-down: widest left half first
-            if j > 0:
-                assert ups and ups[-1][0] + ups[-1][1] == j * nb                   # the lowest update: left half ends right before j
+            srcs = [op[1] // nb for op in t if op[0] == TRACE_UPDATE and op[3] == j]
+            assert srcs == list(range(j))                                         # every block column on the left, in order
             i_f = t.index([TRACE_FACTOR, j, j * nb, min(nb, n - j * nb), 0])
-            assert all(t.index(op) < i_f for op in t if op[0] == TRACE_UPDATE and op[3] == j)
-        sw = [tuple(op[1:]) for op in t if op[0] == TRACE_SWAP_LEFT]
-        assert len(sw) == nblk - 1                                                 # one per internal node of the block tree
-        swaps = swaps or sw
-        assert sw == swaps                                                         # same on every rank, same order
+            assert all(i < i_f for i, op in enumerate(t) if op[0] == TRACE_UPDATE and op[3] == j)
+            for b in range(j):                                                    # a contribution needs its panel
+                i_b = next(i for i, op in enumerate(t) if op[0] == TRACE_BCAST and op[1] == b)
+                i_u = next(i for i, op in enumerate(t) if op[0] == TRACE_UPDATE and op[3] == j and op[1] == b * nb)
+                assert i_b < i_u
+        sw = [(op[3], op[4]) for op in t if op[0] == TRACE_SWAP_LEFT]
+        assert sw == [(b * nb, min(n, (b + 1) * nb)) for b in range(nblk)]         # pivots of every block column, in order

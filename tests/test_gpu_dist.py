@@ -37,7 +37,7 @@ def _free_port():
 
 @pytest.mark.parametrize("g", [1, 2, 4])
 @pytest.mark.parametrize("n,nb,dtype,zero_col", [(1024, 128, np.float64, -1), (1100, 192, np.float64, -1), (2048, 256, np.float64, 700),
-                                                 (1536, 128, np.float32, -1), (640, 64, np.float64, -1)])
+                                                 (1536, 128, np.float32, -1), (640, 64, np.float64, -1), (1920, 64, np.float64, -1)])
 def test_one_process_many_devices_matches_oracle(ctx, g, n, nb, dtype, zero_col):
     """rfb_mg_lu_* on a host matrix: same LU object as rfb200.lu_ -- pivots equal to the oracle's (bit-exact for
     Float64), info equal, ||PA - LU||_F / ||A||_F within 20 n eps; pivots also equal to the single-GPU path's."""
