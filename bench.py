@@ -522,7 +522,10 @@ def run_ours_dist(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rfb200_nccl_%h_%p.log")
     dist.init_process_group("gloo")
     n = args.n if args.n else 32768
-    nb = args.block
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    # block-column width: measured at 32768^2 (profiles/r02_bench_dist*): 8 GPUs are bound by the chain of per-block-column
+    # critical sections (256: 186 ms, 512: 195 ms), 2-4 GPUs by their GEMM share (1024: 307 / 524 ms, 512: 315 / 533 ms)
+    nb = args.block if args.block > 0 else (256 if world_env >= 8 else 1024)
 
     def exchange(mine):
         box = [mine]
@@ -725,7 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", "--n", dest="n", type=int, default=0, help="matrix size (default 16384 on 1 GPU, 32768 distributed)")
-    ap.add_argument("--block", type=int, default=512, help="block-column width of the multi-GPU distribution")
+    ap.add_argument("--block", type=int, default=0, help="block-column width of the multi-GPU distribution (0 = by GPU count)")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")

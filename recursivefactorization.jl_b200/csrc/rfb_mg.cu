@@ -693,7 +693,7 @@ int mg_lu_host(rfb_mg *mg, T *A, int64_t n, int64_t lda, int64_t *ipiv, int64_t 
     if (n < 0 || lda < std::max<int64_t>(n, 1) || !info) return mg_fail(mg, RFB_ERR_ARG, "bad n / lda / info");
     if (n == 0) { *info = 0; return RFB_OK; }
     if (!A || !ipiv) return mg_fail(mg, RFB_ERR_ARG, "A or ipiv is null");
-    if (nb <= 0) nb = 512;
+    if (nb <= 0) nb = n < 8192 ? 256 : (mg->world >= 8 ? 256 : (mg->world >= 5 ? 512 : 1024));   // measured at 32768^2, see bench.py
     if (nb % 64) return mg_fail(mg, RFB_ERR_ARG, "block width must be a multiple of 64");
     int rc = rfb_mg_setup(mg, n, nb, sizeof(T) == 4);
     if (rc != RFB_OK) return rc;

@@ -2,5 +2,5 @@
 mkdir -p gpurun_out
 G=${G:-8}
 run() { tag=$1; shift; (env "$@" timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $((29620 + RANDOM % 200)) bench.py --gpus $G --steps 3 --warmup 2 $EXTRA > gpurun_out/r2_g${G}_$tag.json) 2> gpurun_out/r2_g${G}_$tag.err; }
-run full
-EXTRA="--skip-single --skip-e2e" run cta32 RFB_MG_NCCL_MAX_CTAS=32
+EXTRA="--skip-single --skip-e2e --block 256" run nb256rl
+run full2
