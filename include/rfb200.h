@@ -70,7 +70,9 @@ typedef struct rfb_opts {
     int32_t no_pivot;    /* 1 = pivot = Val(false) / NoPivot() (src/lu.jl:27-65): no row interchanges,
                             `ipiv` may be NULL (NotIPIV) or is filled with 1:min(m,n) (:107-113), a
                             zero pivot is reported as NEGATIVE info (Julia >= 1.11, :24-25, :323-326) */
-    int32_t reserved[9];
+    int32_t keep_factors; /* host-mode rfb_lu_*: 1 = keep the factors + pivots resident on the device after the call so that
+                            rfb_solve_kept_* can solve with them without a second upload (see rfb_kept_id)            */
+    int32_t reserved[8];
 } rfb_opts;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -136,6 +138,14 @@ int rfb_solve_f64(rfb_ctx *ctx, const double *LU, int64_t n, int64_t lda, const 
                   int64_t nrhs, int64_t ldb, const rfb_opts *opts);
 int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const int64_t *ipiv, float *B,
                   int64_t nrhs, int64_t ldb, const rfb_opts *opts);
+
+/* Device-resident factors (`lu` followed by `ldiv!` without uploading the factors a second time).  A host-mode rfb_lu_* with
+ * opts->keep_factors = 1 leaves the square factorization in the context's staging buffer; rfb_kept_id returns its identifier
+ * (0 = nothing resident: any later host-mode call on the context that needs the staging buffer drops it);
+ * rfb_solve_kept_*(ctx, id, B, nrhs, ldb): B (host, n x nrhs) <- U^-1 L^-1 P B like rfb_solve_*, RFB_ERR_ARG if `id` is stale. */
+int rfb_kept_id(rfb_ctx *ctx, int64_t *id);
+int rfb_solve_kept_f64(rfb_ctx *ctx, int64_t id, double *B, int64_t nrhs, int64_t ldb);
+int rfb_solve_kept_f32(rfb_ctx *ctx, int64_t id, float *B, int64_t nrhs, int64_t ldb);
 
 /* ---- pivot = Val(false) and the butterfly solver ---------------------------
  * The NoPivot factorization itself is rfb_lu_* with opts->no_pivot = 1; rfb_solve_* with ipiv == NULL is

@@ -314,6 +314,7 @@ class LU:
 
     def __init__(self, factors: np.ndarray, ipiv: np.ndarray, info: int):
         self.factors, self.ipiv, self.info = factors, ipiv, int(info)
+        self._kept = None                    # (context, id) of a device-resident copy (lu_(..., keep=True))
 
     def __iter__(self):                      # Julia: L, U, p = F
         return iter((self.L, self.U, self.p))
@@ -384,10 +385,11 @@ class AdjointLU:
 # lu / lu!
 # ----------------------------------------------------------------------------------------------
 def _make_opts(mem_space=_lib.RFB_MEM_HOST, leaf_width=0, f32_mode=0, trsm_block=0, gemm_path=0,
-               laswp_path=0, no_pivot=0) -> rfb_opts:
+               laswp_path=0, no_pivot=0, keep_factors=0) -> rfb_opts:
     o = rfb_opts()
     o.mem_space, o.leaf_width, o.f32_mode = mem_space, leaf_width, f32_mode
     o.trsm_block, o.gemm_path, o.laswp_path, o.no_pivot = trsm_block, gemm_path, laswp_path, int(no_pivot)
+    o.keep_factors = int(keep_factors)
     return o
 
 
@@ -413,8 +415,13 @@ def _column_major_lda(A: np.ndarray) -> Optional[int]:
 def lu_(A, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check=True,
         blocksize: Optional[int] = None, threshold: Optional[int] = None, ctx: Optional[Context] = None,
         leaf_width: int = 0, f32_mode: int = 0, trsm_block: int = 0, gemm_path: int = 0,
-        laswp_path: int = 0):
+        laswp_path: int = 0, keep: bool = False):
     """``RecursiveFactorization.lu!`` (src/lu.jl:67-83 and :97-130): factor ``A`` in place.
+
+    ``keep=True`` (square matrices): the factors and pivots also stay resident on the device, and ``ldiv_(F, B)`` /
+    ``F.solve(B)`` then only move ``B`` (``rfb_solve_kept_*``) -- until another host-mode call on the same context reuses
+    the staging buffer, after which they silently go back to uploading ``F.factors``.  The caller promises not to edit
+    ``F.factors`` in between.
 
     ``A`` must be a column-major float64/float32 matrix (it is overwritten with L\\U and returned
     inside the ``LU``); ``ipiv``, if given, must be an int64 vector of length ``min(m, n)`` and is
@@ -456,12 +463,21 @@ def lu_(A, ipiv: Optional[np.ndarray] = None, pivot=True, thread=False, *, check
             raise ValueError(f"ipiv has length {ipiv.size}, expected min(m, n) = {mn}")
     ctx = ctx or default_context()
     info = C.c_int64(0)
-    opts = _make_opts(_lib.RFB_MEM_HOST, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot=not piv)
+    opts = _make_opts(_lib.RFB_MEM_HOST, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot=not piv,
+                      keep_factors=keep)
     ipiv_ptr = ipiv.ctypes.data if (isinstance(ipiv, np.ndarray) and mn) else 0
     ctx.lu_raw(A.ctypes.data if A.size else 0, m, n, lda, ipiv_ptr, C.addressof(info), A.dtype, opts)
+    kept = None
+    if keep:
+        kid = C.c_int64(0)
+        ctx._check(ctx._lib.rfb_kept_id(ctx.handle, C.byref(kid)))
+        if kid.value:
+            kept = (ctx, kid.value)
     if check:
         _checknonsingular(info.value)
-    return LU(A, ipiv, info.value)
+    F = LU(A, ipiv, info.value)
+    F._kept = kept
+    return F
 
 
 def ldiv_(F: LU, B: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
@@ -484,6 +500,15 @@ def ldiv_(F: LU, B: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
         f = np.asfortranarray(f)
         ldf = max(n, 1)
     nrhs = 1 if B.ndim == 1 else B.shape[1]
+    kept = getattr(F, "_kept", None)
+    if kept is not None and (ctx is None or ctx is kept[0]):       # factors still resident on the device: only B travels
+        kctx, kid = kept
+        cur = C.c_int64(0)
+        kctx._check(kctx._lib.rfb_kept_id(kctx.handle, C.byref(cur)))
+        if cur.value == kid:
+            fnk = kctx._lib.rfb_solve_kept_f64 if f.dtype == np.float64 else kctx._lib.rfb_solve_kept_f32
+            kctx._check(fnk(kctx.handle, kid, C.c_void_p(B.ctypes.data), nrhs, ldb))
+            return B
     # NotIPIV: both legs are plain triangular solves, no interchanges (src/lu.jl:60-64)
     ipiv = None if isinstance(F.ipiv, NotIPIV) else np.ascontiguousarray(F.ipiv, dtype=np.int64)
     ctx = ctx or default_context()

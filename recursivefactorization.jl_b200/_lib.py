@@ -31,7 +31,8 @@ class rfb_opts(C.Structure):
         ("gemm_path", C.c_int32),
         ("laswp_path", C.c_int32),
         ("no_pivot", C.c_int32),
-        ("reserved", C.c_int32 * 9),
+        ("keep_factors", C.c_int32),
+        ("reserved", C.c_int32 * 8),
     ]
 
 
@@ -60,6 +61,9 @@ SIGNATURES = {
     "rfb_trsm_lunn_f32": (_int, [_p, _p, _i64, _p, _i64, _i64]),
     "rfb_solve_f64": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, C.POINTER(rfb_opts)]),
     "rfb_solve_f32": (_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i64, C.POINTER(rfb_opts)]),
+    "rfb_kept_id": (_int, [_p, C.POINTER(_i64)]),
+    "rfb_solve_kept_f64": (_int, [_p, _i64, _p, _i64, _i64]),
+    "rfb_solve_kept_f32": (_int, [_p, _i64, _p, _i64, _i64]),
     "rfb_panel_getrf_nopiv_f64": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64]),
     "rfb_panel_getrf_nopiv_f32": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64]),
     "rfb_butterfly_mul_f64": (_int, [_p, _p, _i64, _i64, _p]),

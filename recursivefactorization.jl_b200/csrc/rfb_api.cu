@@ -242,6 +242,7 @@ int solve_entry(rfb_ctx *ctx, const T *LU, int64_t n, int64_t lda, const int64_t
         RFB_TRY(rfb_launch_trsm<T>(ctx, LU, n, B, nrhs, lda, opts));
         return rfb_launch_trsm_upper<T>(ctx, LU, n, B, nrhs, lda, opts);
     }
+    ctx->kept.valid = false;                       // the staging buffer is about to be reused
     const int64_t ldd = (n + 3) & ~int64_t(3);
     const size_t need = sizeof(T) * (size_t)ldd * (size_t)(n + nrhs);
     if (need > ctx->d_mat_cap) {
@@ -313,6 +314,7 @@ int butterfly_solve_entry(rfb_ctx *ctx, const T *A, int64_t n, int64_t lda, T *B
         return rfb_launch_butterfly_vec<T>(ctx, B, n, nrhs, ldb, uv, 1);
     }
     if (space != RFB_MEM_HOST) return ctx->fail(RFB_ERR_ARG, "unknown mem_space %d", space);
+    ctx->kept.valid = false;
     const int64_t np = (n % 4) ? n + (4 - n % 4) : n;      // padded size (:34-38)
     const int64_t ldd = np;
     const size_t need = sizeof(T) * ((size_t)ldd * (size_t)(np + nrhs) + 4 * (size_t)np);
@@ -389,6 +391,7 @@ int lu_batched_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int6
         for (int64_t b = 0; b < batch; ++b) info[b] = 0;
         return RFB_OK;
     }
+    ctx->kept.valid = false;
     const int64_t ldd = (m + 1) & ~int64_t(1);
     const int64_t sdd = ldd * n;
     const size_t need = sizeof(T) * (size_t)sdd * (size_t)batch;
@@ -476,6 +479,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     if (space != RFB_MEM_HOST) return ctx->fail(RFB_ERR_ARG, "unknown mem_space %d", space);
 
     // host pointers: stage through a grow-only device buffer with a dense leading dimension
+    ctx->kept.valid = false;
     const int64_t ldd = (m + 1) & ~int64_t(1);          // even => 16-byte aligned columns for f64
     const size_t need = sizeof(T) * (size_t)ldd * (size_t)n;
     if (need > ctx->d_mat_cap) {
@@ -573,6 +577,47 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
         cudaMemset(&ctx->xchg->error_flag, 0, sizeof(unsigned int));   // report once, keep the context usable
         return ctx->fail(RFB_ERR_INTERNAL, "device-side protocol error (flag set: 1 = panel exchange timed out, 2 = row-exchange lists incomplete)");
     }
+    if (opts && opts->keep_factors && m == n) {          // the factors stay where they are for rfb_solve_kept_*
+        ctx->kept.valid = true;
+        ctx->kept.f32 = sizeof(T) == 4;
+        ctx->kept.nopiv = nopiv;
+        ctx->kept.n = n;
+        ctx->kept.ldd = ldd;
+        ctx->kept.id = ++ctx->kept_counter;
+    }
+    return RFB_OK;
+}
+
+// ldiv!(F, B) with the factors a host-mode rfb_lu_* (keep_factors) left on the device: only B travels
+template <typename T>
+int solve_kept(rfb_ctx *ctx, int64_t id, T *B, int64_t nrhs, int64_t ldb) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (!ctx->kept.valid || ctx->kept.id != id || ctx->kept.f32 != (sizeof(T) == 4))
+        return ctx->fail(RFB_ERR_ARG, "rfb_solve_kept: no factors with id %lld are resident (a later call reused the staging buffer)", (long long)id);
+    const int64_t n = ctx->kept.n, ldd = ctx->kept.ldd;
+    if (nrhs < 0) return ctx->fail(RFB_ERR_ARG, "negative nrhs");
+    if (nrhs == 0 || n == 0) return RFB_OK;
+    if (!B || ldb < n) return ctx->fail(RFB_ERR_ARG, "B is null or ldb < n");
+    RFB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t need = sizeof(T) * (size_t)ldd * (size_t)nrhs;
+    if (need > ctx->d_rhs_cap) {
+        if (ctx->d_rhs) cudaFree(ctx->d_rhs);
+        ctx->d_rhs = nullptr;
+        ctx->d_rhs_cap = 0;
+        if (cudaMalloc(&ctx->d_rhs, need) != cudaSuccess) {
+            cudaGetLastError();
+            return ctx->fail(RFB_ERR_NOMEM, "cannot allocate %zu bytes for the right-hand sides", need);
+        }
+        ctx->d_rhs_cap = need;
+    }
+    const T *dLU = reinterpret_cast<const T *>(ctx->d_mat);
+    T *dB = reinterpret_cast<T *>(ctx->d_rhs);
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(dB, sizeof(T) * ldd, B, sizeof(T) * ldb, sizeof(T) * n, nrhs, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->kept.nopiv) RFB_TRY(rfb_launch_laswp<T>(ctx, dB, nrhs, ldd, ctx->d_ipiv, n, 0));
+    RFB_TRY(rfb_launch_trsm<T>(ctx, dLU, n, dB, nrhs, ldd, &ctx->default_opts));
+    RFB_TRY(rfb_launch_trsm_upper<T>(ctx, dLU, n, dB, nrhs, ldd, &ctx->default_opts));
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(B, sizeof(T) * ldb, dB, sizeof(T) * ldd, sizeof(T) * n, nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RFB_OK;
 }
 
@@ -651,6 +696,7 @@ int rfb_destroy(rfb_ctx *ctx) {
     if (ctx->d_ipiv) cudaFree(ctx->d_ipiv);
     if (ctx->d_binfo) cudaFree(ctx->d_binfo);
     if (ctx->d_mat) cudaFree(ctx->d_mat);
+    if (ctx->d_rhs) cudaFree(ctx->d_rhs);
     if (!ctx->perm_external) {
         if (ctx->perm_dst) cudaFree(ctx->perm_dst);
         if (ctx->perm_src) cudaFree(ctx->perm_src);
@@ -838,6 +884,13 @@ int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const i
                   int64_t ldb, const rfb_opts *opts) {
     return solve_entry<float>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts);
 }
+int rfb_kept_id(rfb_ctx *ctx, int64_t *id) {
+    if (!ctx || !id) return RFB_ERR_ARG;
+    *id = ctx->kept.valid ? ctx->kept.id : 0;
+    return RFB_OK;
+}
+int rfb_solve_kept_f64(rfb_ctx *ctx, int64_t id, double *B, int64_t nrhs, int64_t ldb) { return solve_kept<double>(ctx, id, B, nrhs, ldb); }
+int rfb_solve_kept_f32(rfb_ctx *ctx, int64_t id, float *B, int64_t nrhs, int64_t ldb) { return solve_kept<float>(ctx, id, B, nrhs, ldb); }
 int rfb_panel_getrf_nopiv_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev, int64_t col_offset) {
     RFB_CHECK_CTX(ctx);
     return rfb_launch_panel_nopiv<double>(ctx, A, m, n, lda, info_dev, col_offset);

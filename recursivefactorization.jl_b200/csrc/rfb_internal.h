@@ -64,6 +64,11 @@ struct rfb_ctx {
     int64_t *d_info = nullptr;            // device info word
     void *d_mat = nullptr;                // device matrix for HOST mem_space calls (grow-only)
     size_t d_mat_cap = 0;
+    // factors kept on the device by a host-mode rfb_lu_* with opts->keep_factors (they live in d_mat / d_ipiv)
+    struct { bool valid = false; bool f32 = false, nopiv = false; int64_t n = 0, ldd = 0, id = 0; } kept;
+    int64_t kept_counter = 0;
+    void *d_rhs = nullptr;                // right-hand sides of rfb_solve_kept_* (grow-only)
+    size_t d_rhs_cap = 0;
     int64_t *h_pinned = nullptr;          // pinned scratch (info + small results)
     int64_t *d_binfo = nullptr;           // device info words of host-mode batched calls (grow-only)
     size_t d_binfo_cap = 0;

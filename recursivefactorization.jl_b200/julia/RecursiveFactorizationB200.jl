@@ -35,10 +35,11 @@ struct RfbOpts
     gemm_path::Int32
     laswp_path::Int32
     no_pivot::Int32
-    reserved::NTuple{9, Int32}
+    keep_factors::Int32
+    reserved::NTuple{8, Int32}
 end
-RfbOpts(; mem_space = 0, leaf_width = 0, f32_mode = 0, trsm_block = 0, gemm_path = 0, laswp_path = 0, no_pivot = 0) =
-    RfbOpts(mem_space, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot, ntuple(_ -> Int32(0), 9))
+RfbOpts(; mem_space = 0, leaf_width = 0, f32_mode = 0, trsm_block = 0, gemm_path = 0, laswp_path = 0, no_pivot = 0, keep_factors = 0) =
+    RfbOpts(mem_space, leaf_width, f32_mode, trsm_block, gemm_path, laswp_path, no_pivot, keep_factors, ntuple(_ -> Int32(0), 8))
 
 # src/lu.jl:27-32: the lazy identity pivot vector of an unpivoted factorization
 struct NotIPIV <: AbstractVector{BlasInt}
@@ -103,13 +104,15 @@ function lu!(A::StridedMatrix{T}, ipiv::AbstractVector{<:Integer}, pivot = Val(t
         leaf_width::Integer = 0,                                 # the GPU analogue: columns per panel launch (0 = 64)
         f32_mode::Integer = 0,                                   # RFB_F32_AUTO / TF32X3 / FP32 (include/rfb200.h)
         trsm_block::Integer = 0, gemm_path::Integer = 0, laswp_path::Integer = 0,
+        keep::Bool = false,                                      # leave the factors on the device for ldiv_kept! (rfb_solve_kept_*)
         ctx::Context = default_context()) where {T <: Union{Float64, Float32}}
     piv_on = normalize_pivot(pivot)
     BlasInt === Int64 || error("rfb200 writes Int64 pivots; this Julia has BlasInt = $BlasInt")
     length(ipiv) == min(size(A)...) || throw(DimensionMismatch("ipiv must have length min(m, n)"))
     piv = (ipiv isa Vector{BlasInt} || ipiv isa NotIPIV) ? ipiv : Vector{BlasInt}(undef, length(ipiv))
     info = _rfb_lu!(ctx, A, piv, RfbOpts(leaf_width = leaf_width, f32_mode = f32_mode, trsm_block = trsm_block,
-                                         gemm_path = gemm_path, laswp_path = laswp_path, no_pivot = piv_on ? 0 : 1))
+                                         gemm_path = gemm_path, laswp_path = laswp_path, no_pivot = piv_on ? 0 : 1,
+                                         keep_factors = keep ? 1 : 0))
     piv === ipiv || copyto!(ipiv, piv)
     _wants_check(check) && checknonsingular(info)                # SingularException / ZeroPivotException, src/lu.jl:128
     return LU(A, ipiv, BlasInt(info))                            # src/lu.jl:129
@@ -206,6 +209,24 @@ for (T, solve, bsolve, batched) in ((Float64, :rfb_solve_f64, :rfb_butterfly_sol
             check && foreach(checknonsingular, info)
             return [LU(view(A, :, :, b), view(ipiv, :, b), BlasInt(info[b])) for b in 1:batch]
         end
+    end
+end
+
+# `ldiv!` with the factors that `lu!(A, ipiv; keep = true)` left on the device (only B travels).  `kept_id(ctx)` right after
+# the factorization identifies them; a stale id (another host-mode call reused the staging buffer) is an error here -- fall
+# back to ldiv_gpu!(F, B).
+function kept_id(ctx::Context = default_context())
+    id = Ref{Int64}(0)
+    _chk_rc(ctx, ccall((:rfb_kept_id, librfb200), Cint, (Ptr{Cvoid}, Ptr{Int64}), ctx.handle, id))
+    return id[]
+end
+_chk_rc(ctx, rc) = rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+for (T, sym) in ((Float64, :rfb_solve_kept_f64), (Float32, :rfb_solve_kept_f32))
+    @eval function ldiv_kept!(id::Integer, B::StridedVecOrMat{$T}; ctx::Context = default_context())
+        stride(B, 1) == 1 || throw(ArgumentError("rfb200 needs unit row stride"))
+        _chk_rc(ctx, GC.@preserve B ccall(($(QuoteNode(sym)), librfb200), Cint, (Ptr{Cvoid}, Int64, Ptr{$T}, Int64, Int64),
+            ctx.handle, id, pointer(B), size(B, 2), B isa AbstractVector ? max(1, length(B)) : max(1, stride(B, 2))))
+        return B
     end
 end
 

@@ -263,3 +263,36 @@ def test_batched_throughput_shape_16k(ctx):
     for b in (0, 1, 8191, 16383):
         want_f, want_p, _ = O.panel_c(np.asfortranarray(a0[b]))
         assert np.array_equal(Fs[b].ipiv, want_p) and np.array_equal(Fs[b].factors, want_f)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("pivot", [True, False])
+def test_ldiv_with_device_resident_factors(ctx, dtype, pivot):
+    """`lu_(A, keep=True)` leaves the factors on the device; `ldiv_` then only moves B (rfb_solve_kept_*) and must give
+    exactly what the uploading path gives; once another host-mode call has reused the staging buffer the kept id is
+    stale and `ldiv_` silently goes back to uploading F.factors."""
+    n = 700
+    rng = np.random.default_rng([71, n, int(pivot)])
+    a0 = rand_matrix(rng, n, n, dtype)
+    if not pivot:
+        a0[np.arange(n), np.arange(n)] += dtype(n / 4)
+    b = rand_matrix(rng, n, 5, dtype)
+    F = rfb200.lu_(a0.copy(order="F"), None, pivot, ctx=ctx, keep=True)
+    assert F._kept is not None
+    before = ctx.launch_count()
+    x_kept = rfb200.ldiv_(F, b.copy(order="F"), ctx=ctx)
+    kid = C.c_int64(0)
+    ctx._check(ctx._lib.rfb_kept_id(ctx.handle, C.byref(kid)))
+    assert kid.value == F._kept[1] and ctx.launch_count() > before           # still resident after the solve
+    G = rfb200.LU(F.factors, F.ipiv, F.info)                                  # no kept handle: the uploading path
+    x_up = rfb200.ldiv_(G, b.copy(order="F"), ctx=ctx)
+    assert np.array_equal(x_kept, x_up)
+    ctx._check(ctx._lib.rfb_kept_id(ctx.handle, C.byref(kid)))
+    assert kid.value == 0                                                     # the upload reused the staging buffer
+    x_again = rfb200.ldiv_(F, b.copy(order="F"), ctx=ctx)                     # stale id -> falls back, same answer
+    assert np.array_equal(x_again, x_up)
+    v = rfb200.ldiv_(rfb200.lu_(a0.copy(order="F"), None, pivot, ctx=ctx, keep=True), b[:, 0].copy(), ctx=ctx)
+    assert np.array_equal(v, x_up[:, 0]) or np.allclose(v, x_up[:, 0], rtol=0, atol=1000 * n * np.finfo(dtype).eps)
+    with pytest.raises(rfb200.RfbError):
+        fnk = ctx._lib.rfb_solve_kept_f64 if dtype == np.float64 else ctx._lib.rfb_solve_kept_f32
+        ctx._check(fnk(ctx.handle, 123456789, C.c_void_p(b.ctypes.data), 5, n))
