@@ -191,23 +191,36 @@ def run_reference(args, rank, world):
         return
     from oracle import rf_oracle as O
     cores = os.cpu_count() or 1
+    t_start = time.perf_counter()
     cpu_baseline(2048, cores)                         # first call: thread pool start-up, page faults
-    gf_cal, _ = cpu_baseline(4096, cores)             # calibration (the port's rate still grows a little beyond this size)
-    budget_s = args.ref_budget_s / max(1, args.steps + args.warmup)
-    n_s = 2048
-    for cand in (3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768):
-        if cand <= args.n and lu_flops(cand) / (gf_cal * 1e9) <= budget_s:
-            n_s = cand
-    if lu_flops(args.n) / (gf_cal * 1e9) <= budget_s:
-        n_s = args.n
-    a0 = np.empty((n_s, n_s), dtype=np.float64, order="F")
-    fill_random(a0)
-    times = []
-    for it in range(args.warmup + args.steps):
+    gf_cal, _ = cpu_baseline(4096, cores)             # optimistic calibration (only used to skip hopeless sizes)
+    total = max(1, args.steps + args.warmup)
+    # Largest size whose `steps + warmup` factorizations fit the budget, decided on a MEASURED factorization at that size:
+    # the first one (a warm-up when there is one) is timed, and the size is kept only if the projection fits what is left.
+    n_s, a0, done = None, None, []
+    for cand in [args.n] + [c for c in (24576, 16384, 12288, 8192, 6144, 4096, 3072, 2048) if c < args.n]:
+        left = args.ref_budget_s - (time.perf_counter() - t_start)
+        if cand > 2048 and lu_flops(cand) / (gf_cal * 1e9) * total > left:
+            continue
+        a0 = np.empty((cand, cand), dtype=np.float64, order="F")
+        fill_random(a0)
         a = a0.copy(order="F")
         t = time.perf_counter()
         O.lu_c(a, threads=cores)
         dt = time.perf_counter() - t
+        left = args.ref_budget_s - (time.perf_counter() - t_start)
+        if cand <= 2048 or dt * (total - 1) <= left:
+            n_s, done = cand, [dt]
+            break
+    times = []
+    for it in range(args.warmup + args.steps):
+        if it == 0 and done:
+            dt = done[0]                              # the probe above was this first factorization
+        else:
+            a = a0.copy(order="F")
+            t = time.perf_counter()
+            O.lu_c(a, threads=cores)
+            dt = time.perf_counter() - t
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
@@ -738,7 +751,7 @@ def main():
     ap.add_argument("--check-pivots", dest="check_pivots", action="store_true", default=True,
                     help="compare the pivot vector of the timed factorization with LAPACK dgetrf (default: on)")
     ap.add_argument("--no-check-pivots", dest="check_pivots", action="store_false")
-    ap.add_argument("--ref-budget-s", type=float, default=900.0,
+    ap.add_argument("--ref-budget-s", type=float, default=1500.0,
                     help="reference arm: wall-clock budget for all its factorizations; the arm runs the same size as the "
                          "product arm when that fits")
     args = ap.parse_args()
