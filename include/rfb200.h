@@ -83,6 +83,12 @@ const char *rfb_last_error(rfb_ctx *ctx);             /* valid until the next ca
 int rfb_device_info(rfb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *mem_bytes);
 /* options used by the kernel-level calls below (which take no rfb_opts); NULL restores defaults */
 int rfb_set_default_opts(rfb_ctx *ctx, const rfb_opts *opts);
+/* Host-mode rfb_lu_* on a PAGE-LOCKED caller matrix send finished parts of the factors back while the factorization
+ * is still running (results are identical; only the time at which host memory is written changes):
+ *   2 = finished tiles (default): every 512-column unit's row band and every node's U12 block as soon as it is final,
+ *   1 = row bands at the right spine of the recursion, 0 = off (one download at the end, reference interchange order).
+ * Environment RFB_EARLY_DOWNLOAD sets the initial value. */
+int rfb_set_early_download(rfb_ctx *ctx, int mode);
 
 /* ---- whole path: twin of lu!(A, ipiv, Val(true), thread; check=false)  src/lu.jl:97-156 ----
  * Factors the m x n matrix in place (L strictly below the diagonal, U on/above: the layout of
@@ -268,11 +274,13 @@ int rfb_mg_trace(int64_t n, int64_t block, int rank, int world, int64_t *ops, in
  * Runs the host recursion of rfb_lu_* (twin of src/lu.jl:97-156 and :189-263) for an m x n matrix WITHOUT launching
  * anything and returns the sequence of operations it would enqueue, 8 int64 per operation:
  *   [0] op: 1 panel getrf (src/lu.jl:290-338), 2 unpivoted panel, 3 row interchanges (:164-188), 4 unit-lower TRSM
- *       (:235, :153), 5 Schur update (:265-284), 6 early download of finished rows (host mode), 7 identity ipiv fill
- *   [1],[2] row, column of the first operand (panel / swapped block / L / C); [6],[7] of the second (B of the TRSM,
- *       A of the update, whose B is at row [7], column [2]);  [3],[4],[5] sizes: panel m, n, column offset; laswp
- *       ncols, first pivot, one past the last pivot; TRSM k, nrhs; update m, n, k; download first row ([1]), rows, cols.
- * `pinned_host` selects the schedule used for page-locked host matrices (eager interchanges + early row downloads).
+ *       (:235, :153), 5 Schur update (:265-284), 6 early download of a finished tile (host mode), 7 identity ipiv fill
+ *   [1],[2] row, column of the first operand (panel / swapped block / L / C / downloaded tile); [6],[7] of the second
+ *       (B of the TRSM, A of the update, whose B is at row [7], column [2]);  [3],[4],[5] sizes: panel m, n, column
+ *       offset; laswp ncols, first pivot, one past the last pivot; TRSM k, nrhs; update m, n, k; download rows, cols.
+ * `pinned_host` selects the schedule used for page-locked host matrices: eager interchanges + early downloads of
+ *   finished tiles (pinned_host = 1: the library default, environment RFB_EARLY_DOWNLOAD = 0 off / 1 row bands at
+ *   the right spine / 2 tiles; pinned_host = 10 + mode forces a mode).
  * Used by the CPU tests to replay the schedule with the oracle's kernels and compare with the oracle's own LU. */
 int rfb_trace_lu(int is_f32, int64_t m, int64_t n, int64_t lda, const rfb_opts *opts, int pinned_host, int64_t *ops,
                  int64_t cap, int64_t *count);

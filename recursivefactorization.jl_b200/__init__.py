@@ -210,6 +210,11 @@ class Context:
         else:
             self._check(self._lib.rfb_set_default_opts(self._h, None))
 
+    def set_early_download(self, mode: int):
+        """How `lu_` on a page-locked matrix sends finished factors back while it is still factoring
+        (`rfb_set_early_download`): 2 finished tiles (default), 1 row bands at the right spine, 0 off."""
+        self._check(self._lib.rfb_set_early_download(self._h, int(mode)))
+
     def malloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self._lib.rfb_malloc(self._h, C.byref(p), nbytes))
@@ -531,9 +536,13 @@ def lu(A, pivot=True, thread=False, **kwargs):
     return lu_(np.array(A, order="F", copy=True), None, pivot, thread, **kwargs)
 
 
-def trace_lu(m: int, n: int, dtype=np.float64, pinned_host: bool = False, lda: Optional[int] = None, **opt_kw) -> np.ndarray:
+def trace_lu(m: int, n: int, dtype=np.float64, pinned_host: bool = False, lda: Optional[int] = None,
+             early_mode: Optional[int] = None, **opt_kw) -> np.ndarray:
     """The launch sequence `rfb_lu_*` would enqueue for an m x n matrix, without a GPU (`rfb_trace_lu`): an (nops, 8)
-    int64 array, see include/rfb200.h.  `pinned_host=True` gives the schedule used for page-locked host matrices."""
+    int64 array, see include/rfb200.h.  `pinned_host=True` gives the schedule used for page-locked host matrices;
+    `early_mode` (0 off, 1 row bands, 2 tiles) forces one of its early-download schemes instead of the default."""
+    if pinned_host and early_mode is not None:
+        pinned_host = 10 + int(early_mode)
     lib = _lib.load()
     lda = lda if lda is not None else max(m, 1)
     opts = _make_opts(_lib.RFB_MEM_DEVICE, **opt_kw)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "rfb_last_error": (C.c_char_p, [_p]),
     "rfb_device_info": (_int, [_p, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(C.c_size_t)]),
     "rfb_set_default_opts": (_int, [_p, C.POINTER(rfb_opts)]),
+    "rfb_set_early_download": (_int, [_p, _int]),
     "rfb_lu_f64": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_lu_f32": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, C.POINTER(rfb_opts)]),
     "rfb_panel_getrf_f64": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p, _i64]),

@@ -33,7 +33,9 @@ struct LuPlan {
     // early download (host mode): rows [0, n1) of the root are final long before the factorization ends
     void *host_A = nullptr;            // caller's matrix (host), nullptr in device mode
     int64_t host_lda = 0, host_m = 0;
-    int64_t early_rows = 0;            // rows [0, early_rows) of ALL columns were already sent back (copy stream)
+    int early_mode = 0;                // 0 = one download at the end, 1 = row bands at the right spine, 2 = finished tiles
+    int64_t early_rows = 0;            // mode 1: rows [0, early_rows) of ALL columns were already sent back (download stream)
+    bool tiles_done = false;           // mode 2: every element has been sent back tile by tile
     int64_t n_total = 0;               // columns of the whole matrix
     // pipelined upload (host mode): column chunk i is resident once up_events[i] has fired
     std::vector<cudaEvent_t> *up_events = nullptr;
@@ -66,14 +68,42 @@ int lu_swap(rfb_ctx *ctx, T *A, int64_t ncols, int64_t lda, const int64_t *ipiv,
 //
 // eager_left < 0: the reference's own order -- the interchanges of the right half reach the columns to
 //   their left when the node finishes (`apply_permutation!(P2, A21)`, :246).
-// eager_left >= 0 (pinned host matrices): every finished subtree of at most kEagerUnit columns applies its
+// eager_left >= 0 (pinned host matrices): every finished subtree of at most kEagerUnit columns (a "unit") applies its
 //   interchanges to ALL columns [eager_left, c0) on its left at once, so :246 has nothing left to do at the
 //   nodes above it.  Each column still receives every later pivot exactly once and in pivot order, so the
-//   result is identical; what changes is WHEN rows become final: after the swap + TRSM of a node on the
-//   right spine, rows [c0, c0 + n1) of every column are final and start travelling back to the host while
-//   the trailing update runs, instead of waiting for the end of the factorization.
+//   result is identical; what changes is WHEN elements become final, and final elements travel back to the host
+//   while the factorization is still running (download stream) instead of waiting for its end:
+//     mode 2 (default, "tiles"): when unit [c0, c0 + w) has applied its interchanges, rows [c0, c0 + w) of columns
+//       [0, c0 + w) are final (L on the left, the unit's own L\U block; every later pivot only touches rows >= c0 + w);
+//       when ANY node above unit level has done its swap + TRSM, its U12 block -- rows [c0, c0 + n1) of columns
+//       [c0 + n1, c0 + n) -- is final (later pivots live below it, ancestors only read it).  Row r and column j > r's
+//       unit meet in exactly one such node (the lowest common ancestor of their units), so the tiles cover the matrix
+//       exactly once; the last unit takes the rows below the square part with it.  The L half of the matrix -- which a
+//       row-band scheme can only release when the right spine passes -- leaves evenly, unit by unit, and only the last
+//       unit's band (w x n) is still to be sent when the last panel finishes.
+//     mode 1 ("row bands", round 1): after the swap + TRSM of a node on the right spine, rows [c0, c0 + n1) of every
+//       column are final; the bands halve while the PCIe time of what is left does not shrink as fast as the compute
+//       time, so the last quarter of the rows arrives ~6 ms after the last panel at 16384^2.
 constexpr int64_t kEagerUnit = 512;
 constexpr int64_t kEarlyRowsMin = 256;
+
+// Early download (host mode): rows [r0, r0 + nr) x columns [j0, j0 + nc) are final on the device.
+template <typename T>
+int early_download(rfb_ctx *ctx, LuPlan &plan, T *root, int64_t lda, int64_t r0, int64_t nr, int64_t j0, int64_t nc) {
+    if (nr <= 0 || nc <= 0) return RFB_OK;
+    if (ctx->dry_run) {
+        RfbTraceOp o{};
+        o.v[0] = RFB_T_DOWNLOAD; o.v[1] = r0; o.v[2] = j0; o.v[3] = nr; o.v[4] = nc;
+        ctx->trace.push_back(o);
+        return RFB_OK;
+    }
+    RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
+    RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->down_stream, ctx->ev_sync, 0));
+    RFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<T *>(plan.host_A) + r0 + j0 * plan.host_lda, sizeof(T) * plan.host_lda,
+                                    root + r0 + j0 * lda, sizeof(T) * lda, sizeof(T) * nr, nc, cudaMemcpyDeviceToHost,
+                                    ctx->down_stream));
+    return RFB_OK;
+}
 
 template <typename T>
 int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n, int64_t *ipiv, int64_t *info,
@@ -84,6 +114,13 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
         RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0, n, ipiv, info, plan, -1));
         if (plan.pivot && c0 > eager_left)
             RFB_TRY(lu_swap<T>(ctx, root + c0 + eager_left * lda, c0 - eager_left, lda, ipiv, c0, n, plan));
+        if (plan.host_A && plan.early_mode == 2 && eager_left == 0) {
+            // the unit's band: L of all columns on its left + its own L\U block; the last unit also carries the rows
+            // below the square part (tall matrices) and closes the tiling
+            const bool last = c0 + n == plan.n_total;
+            RFB_TRY(early_download<T>(ctx, plan, root, lda, c0, last ? m - c0 : n, 0, c0 + n));
+            if (last) plan.tiles_done = true;
+        }
         return RFB_OK;
     }
     if (n <= plan.leaf) {                 // :192-195 leaf -> K1
@@ -97,21 +134,14 @@ int lu_rec(rfb_ctx *ctx, T *root, int64_t m, int64_t lda, int64_t c0, int64_t n,
     RFB_TRY(need_cols(ctx, plan, c0 + n));
     if (plan.pivot) RFB_TRY(lu_swap<T>(ctx, AR, n2, lda, ipiv, c0, n1, plan));          // :233
     RFB_TRY(rfb_launch_trsm<T>(ctx, A, n1, AR, n2, lda, plan.opts));                    // :235
-    if (plan.host_A && eager_left == 0 && c0 == plan.early_rows && c0 + n == plan.n_total && n1 >= kEarlyRowsMin) {
+    if (plan.host_A && eager_left == 0 && plan.early_mode == 2) {
+        RFB_TRY(early_download<T>(ctx, plan, root, lda, c0, n1, c0 + n1, n2));          // this node's U12 is final
+    } else if (plan.host_A && eager_left == 0 && plan.early_mode == 1 && c0 == plan.early_rows && c0 + n == plan.n_total &&
+               n1 >= kEarlyRowsMin) {
         // right-spine node, pinned host matrix: rows [c0, c0 + n1) of ALL columns are final now (L and U11 on the
         // left, U12 on the right; everything still to come touches rows >= c0 + n1 only).
-        if (ctx->dry_run) {
-            RfbTraceOp o{};
-            o.v[0] = RFB_T_DOWNLOAD_ROWS; o.v[1] = c0; o.v[3] = n1; o.v[4] = plan.n_total;
-            ctx->trace.push_back(o);
-            plan.early_rows = c0 + n1;
-        } else {
-        RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
-        RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
-        RFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<T *>(plan.host_A) + c0, sizeof(T) * plan.host_lda, root + c0,
-                                        sizeof(T) * lda, sizeof(T) * n1, plan.n_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        RFB_TRY(early_download<T>(ctx, plan, root, lda, c0, n1, 0, plan.n_total));
         plan.early_rows = c0 + n1;
-        }
     }
     RFB_TRY(rfb_launch_gemm<T>(ctx, AR + n1, A + n1, AR, mm - n1, n2, n1, lda, plan.opts));   // :240
     RFB_TRY(lu_rec<T>(ctx, root, m, lda, c0 + n1, n2, ipiv, info, plan, eager_left));   // :244
@@ -133,6 +163,7 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
     plan.up_events = up_events;
     plan.up_bounds = up_bounds;
     plan.host_A = host_A;
+    plan.early_mode = host_A ? ctx->early_mode : 0;
     plan.host_lda = host_lda;
     plan.host_m = m;
     plan.rows = m;
@@ -171,14 +202,14 @@ int lu_device(rfb_ctx *ctx, T *dA, int64_t m, int64_t n, int64_t lda, int64_t *d
         RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_dst, 0xFF, 2 * (size_t)mn * sizeof(int), ctx->stream));
         RFB_CUDA(ctx, cudaMemsetAsync(ctx->perm_width, 0, (size_t)mn * sizeof(int), ctx->stream));
     }
-    RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan, (host_A && m >= n) ? 0 : -1));   // :147
+    RFB_TRY(lu_rec<T>(ctx, dA, m, lda, 0, mn, d_ipiv, d_info, plan, (host_A && m >= n && plan.early_mode != 0) ? 0 : -1));   // :147
     if (m < n) {                                                                        // :148-154
         T *AR = dA + m * lda;
         RFB_TRY(need_cols(ctx, plan, n));
         if (plan.pivot) RFB_TRY(lu_swap<T>(ctx, AR, n - m, lda, d_ipiv, 0, mn, plan));
         RFB_TRY(rfb_launch_trsm<T>(ctx, dA, m, AR, n - m, lda, opts));
     }
-    if (early_rows) *early_rows = plan.early_rows;
+    if (early_rows) *early_rows = plan.tiles_done ? m : plan.early_rows;     // tiles: nothing is left to download
     return RFB_OK;
 }
 
@@ -546,19 +577,20 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
             // uploads from / early downloads into the caller's matrix may still be in flight: the library never keeps a
             // host pointer past the call, so drain both streams before reporting the failure
             cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->down_stream);
             cudaStreamSynchronize(ctx->stream);
             cudaGetLastError();
             return rc;
         }
     }
     RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evs[nchunks - 1], 0));   // (already implied; keeps the order explicit)
-    // download what the early copies (rows [0, early_rows) of all columns) did not cover
+    // download what the early copies (rows [0, early_rows) of all columns; everything in tile mode) did not cover
     if (early_rows > 0) {
         if (early_rows < m)
             RFB_CUDA(ctx, cudaMemcpy2DAsync(A + early_rows, sizeof(T) * lda, dA + early_rows, sizeof(T) * ldd,
                                             sizeof(T) * (m - early_rows), n, cudaMemcpyDeviceToHost, ctx->stream));
-        RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->copy_stream));
-        RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));    // the early copy must be done before we return
+        RFB_CUDA(ctx, cudaEventRecord(ctx->ev_sync, ctx->down_stream));
+        RFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));    // the early copies must be done before we return
     } else {
         RFB_CUDA(ctx, cudaMemcpy2DAsync(A, sizeof(T) * lda, dA, sizeof(T) * ldd, sizeof(T) * m, n,
                                         cudaMemcpyDeviceToHost, ctx->stream));
@@ -652,6 +684,9 @@ int rfb_create(rfb_ctx **out, int device) {
     RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    RFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("RFB_EARLY_DOWNLOAD")) ctx->early_mode = atoi(e);      // A/B switch, see lu_rec
+    if (ctx->early_mode < 0 || ctx->early_mode > 2) ctx->early_mode = 2;
     RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
     RFB_CUDA(ctx, cudaEventCreate(&ctx->ev_stop));
     RFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
@@ -708,6 +743,7 @@ int rfb_destroy(rfb_ctx *ctx) {
     if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     delete ctx;
     return RFB_OK;
 }
@@ -730,6 +766,13 @@ int rfb_set_default_opts(rfb_ctx *ctx, const rfb_opts *opts) {
     return RFB_OK;
 }
 
+int rfb_set_early_download(rfb_ctx *ctx, int mode) {
+    if (!ctx) return RFB_ERR_ARG;
+    if (mode < 0 || mode > 2) return ctx->fail(RFB_ERR_ARG, "early-download mode must be 0, 1 or 2 (got %d)", mode);
+    ctx->early_mode = mode;
+    return RFB_OK;
+}
+
 int rfb_trace_lu(int is_f32, int64_t m, int64_t n, int64_t lda, const rfb_opts *opts, int pinned_host, int64_t *ops,
                  int64_t cap, int64_t *count) {
     if (!count || m < 0 || n < 0 || lda < (m > 1 ? m : 1)) return RFB_ERR_ARG;
@@ -739,6 +782,9 @@ int rfb_trace_lu(int is_f32, int64_t m, int64_t n, int64_t lda, const rfb_opts *
     ctx.trace_elt = is_f32 ? 4 : 8;
     char *base = reinterpret_cast<char *>(uintptr_t(1) << 40);       // fake address, never dereferenced
     ctx.trace_base = base;
+    if (const char *e = getenv("RFB_EARLY_DOWNLOAD")) ctx.early_mode = atoi(e);
+    if (pinned_host >= 10) ctx.early_mode = pinned_host - 10;
+    if (ctx.early_mode < 0 || ctx.early_mode > 2) ctx.early_mode = 2;
     int64_t *fake_piv = reinterpret_cast<int64_t *>(uintptr_t(1) << 39);
     int rc;
     if (is_f32) {

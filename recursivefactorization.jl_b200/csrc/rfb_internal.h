@@ -37,7 +37,7 @@ struct RfbPanelXchg {
 // Dry-run trace of the host driver (rfb_trace_lu): the launchers record what they WOULD launch instead of
 // launching it, so the recursion of rfb_api.cu can be replayed and checked on a machine without a GPU.
 enum RfbTraceOpCode { RFB_T_PANEL = 1, RFB_T_PANEL_NOPIV = 2, RFB_T_LASWP = 3, RFB_T_TRSM_LOWER = 4, RFB_T_GEMM = 5,
-                      RFB_T_DOWNLOAD_ROWS = 6, RFB_T_IOTA = 7 };
+                      RFB_T_DOWNLOAD = 6, RFB_T_IOTA = 7 };
 struct RfbTraceOp {
     int64_t v[8];   // v[0] = op code; operands are (row, col) offsets into the traced matrix and sizes (see rfb200.h)
 };
@@ -51,7 +51,9 @@ struct rfb_ctx {
     size_t mem_bytes = 0;
     cudaStream_t stream = nullptr;        // stream everything is enqueued on
     cudaStream_t own_stream = nullptr;    // the stream created with the context
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device uploads of host-mode calls
+    cudaStream_t down_stream = nullptr;   // device -> host early downloads (its own stream: the two copy engines overlap)
+    int early_mode = 2;                   // early download of pinned host matrices: 0 off, 1 row bands, 2 tiles (rfb_api.cu)
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_sync = nullptr;
     std::string last_error;
     rfb_opts default_opts = {};           // used by kernel-level ABI calls

@@ -204,26 +204,37 @@ def test_baseline_config_f32_8192_tensor_core(ctx):
 
 @pytest.mark.parametrize("dtype,shape", [(np.float64, (4096, 4096)), (np.float64, (3000, 3000)), (np.float64, (5000, 2500)),
                                          (np.float32, (4100, 4100)), (np.float64, (2048, 2600)), (np.float64, (1500, 1500))])
-def test_pinned_host_matrix_early_download(ctx, dtype, shape):
+@pytest.mark.parametrize("mode", [2, 1, 0])
+def test_pinned_host_matrix_early_download(ctx, dtype, shape, mode):
     """Page-locked caller matrix: the upload is pipelined, finished subtrees apply their interchanges to all
-    columns on their left at once (instead of at the end of each node, src/lu.jl:246), and the rows of every
-    right-spine node travel back to the host while its trailing update still runs.  Same swaps in the same
-    per-column order: the result must be IDENTICAL to the pageable-path result (reference order)."""
+    columns on their left at once (instead of at the end of each node, src/lu.jl:246), and finished parts of the
+    factors travel back to the host while the factorization still runs -- tile by tile (mode 2, the default: unit row
+    bands + U12 blocks on a download stream of their own), as row bands of the right-spine nodes (mode 1), or not at
+    all (mode 0).  Same swaps in the same per-column order: the result must be IDENTICAL to the pageable-path result
+    (reference order), and every element must have arrived (the host matrix is poisoned first)."""
     m, n = shape
     a0 = rand_matrix(np.random.default_rng([77, m, n]), m, n, dtype)
     F_ref = rfb200.lu(a0, ctx=ctx)                       # pageable numpy memory
     a_pin = ctx.pinned_empty((m, n), dtype)
-    np.copyto(a_pin, a0)
-    ipiv = np.empty(min(m, n), dtype=np.int64)
-    F = rfb200.lu_(a_pin, ipiv, ctx=ctx)
-    assert F.info == 0
-    assert np.array_equal(F.ipiv, F_ref.ipiv)
-    assert np.array_equal(np.asarray(F.factors), F_ref.factors)
-    # and without pivoting (no interchanges to move, downloads only)
-    G_ref = rfb200.lu(a0 + 10 * np.eye(m, n, dtype=dtype), False, ctx=ctx)
-    np.copyto(a_pin, a0 + 10 * np.eye(m, n, dtype=dtype))
-    G = rfb200.lu_(a_pin, None, False, ctx=ctx)
-    assert np.array_equal(np.asarray(G.factors), G_ref.factors)
+    ctx.set_early_download(mode)
+    try:
+        np.copyto(a_pin, a0)
+        ipiv = np.empty(min(m, n), dtype=np.int64)
+        F = rfb200.lu_(a_pin, ipiv, ctx=ctx)
+        assert F.info == 0
+        assert np.array_equal(F.ipiv, F_ref.ipiv)
+        assert np.array_equal(np.asarray(F.factors), F_ref.factors)
+        # and without pivoting (no interchanges to move, downloads only)
+        G_ref = rfb200.lu(a0 + 10 * np.eye(m, n, dtype=dtype), False, ctx=ctx)
+        np.copyto(a_pin, a0 + 10 * np.eye(m, n, dtype=dtype))
+        G = rfb200.lu_(a_pin, None, False, ctx=ctx)
+        assert np.array_equal(np.asarray(G.factors), G_ref.factors)
+        # twice in a row on the same buffers: the second call's upload must not overtake the first call's downloads
+        np.copyto(a_pin, a0)
+        F2 = rfb200.lu_(a_pin, ipiv, ctx=ctx)
+        assert np.array_equal(np.asarray(F2.factors), F_ref.factors)
+    finally:
+        ctx.set_early_download(2)
 
 
 @pytest.mark.parametrize("shape", [(50000, 48), (90000, 24), (40000, 200)])

@@ -47,9 +47,9 @@ def replay(a, ops, pivot=True):
             O.trsm_c(a, (r, c), s0, (r2, c2), s1)
         elif op == GEMM:
             O.schur_c(a, (r, c), (r2, c2), (c2, c), s0, s1, s2)
-        elif op == DOWNLOAD:
-            assert s1 == n
-            snapshots.append((r, s0, a[r:r + s0, :].copy()))
+        elif op == DOWNLOAD:                                  # tile rows [r, r + s0) x columns [c, c + s1)
+            assert 0 <= r and r + s0 <= m and 0 <= c and c + s1 <= n and s0 > 0 and s1 > 0
+            snapshots.append((r, c, a[r:r + s0, c:c + s1].copy()))
         elif op == IOTA:
             ipiv[:] = np.arange(1, mn + 1)
         else:
@@ -61,28 +61,65 @@ CASES = [(1, 1), (5, 7), (64, 64), (65, 65), (130, 130), (300, 300), (300, 302),
          (777, 777), (1100, 1100)]
 
 
+def check_early_downloads(snaps, got, mode):
+    """Every early download must have seen elements that never change afterwards, and no element may travel twice.
+    Mode 2 (tiles) covers the whole matrix; mode 1 (row bands) covers full-width bands contiguous from row 0."""
+    m, n = got.shape
+    seen = np.zeros((m, n), dtype=np.int32)
+    for r, c, block in snaps:
+        assert np.array_equal(block, got[r:r + block.shape[0], c:c + block.shape[1]], equal_nan=True), (r, c, block.shape)
+        seen[r:r + block.shape[0], c:c + block.shape[1]] += 1
+    assert seen.max(initial=0) <= 1, "an element was downloaded twice"
+    if mode == 2 and snaps:
+        assert seen.min() == 1, "tile mode must cover the whole matrix (nothing is downloaded at the end)"
+    if mode == 1:
+        covered = 0
+        for r, c, block in snaps:
+            assert r == covered and c == 0 and block.shape[1] == n
+            covered += block.shape[0]
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", CASES)
-@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("pinned", [0, 1, 2])                  # pageable / page-locked with row bands / with tiles
 def test_pivoted_schedule_replays_to_the_oracle_lu(dtype, shape, pinned):
     m, n = shape
     a0 = rand_matrix(np.random.default_rng([41, m, n]), m, n, dtype)
     if m > 200:
         a0[:, 150] = 0                                        # a zero pivot somewhere in the middle: info path
-    ops = rfb200.trace_lu(m, n, dtype, pinned_host=pinned)
+    ops = rfb200.trace_lu(m, n, dtype, pinned_host=bool(pinned), early_mode=pinned or None)
     got, ipiv, info, snaps = replay(a0.copy(order="F"), ops)
     want, wp, winfo = O.lu_c(a0.copy(order="F"), blocksize=64, threshold=1)
     assert info == winfo and np.array_equal(ipiv, wp)
     assert np.array_equal(got, want, equal_nan=True)
-    if pinned and m >= n and n >= 1024:
-        assert snaps, "a large page-locked square/tall matrix must download rows early"
-    covered = 0
-    for r, nrows, block in snaps:                             # early downloads: contiguous from row 0, rows already final
-        assert r == covered
-        covered += nrows
-        assert np.array_equal(block, got[r:r + nrows, :], equal_nan=True)
-    if not pinned:
+    if pinned and m >= n and (n >= 1024 or pinned == 2):
+        assert snaps, "a page-locked square/tall matrix must send finished elements back early"
+    check_early_downloads(snaps, got, pinned)
+    if not pinned or m < n:
         assert not snaps
+
+
+@pytest.mark.parametrize("shape", [(1536, 1536), (2100, 1700), (1024, 1024), (513, 513), (512, 512), (3000, 600)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_early_download_modes_tile_the_matrix(shape, mode):
+    """Units of 512 columns: several units, ragged last unit, tall matrices (rows below the square part leave with the
+    last unit), a single unit.  Mode 0 keeps the reference's interchange order and downloads nothing early."""
+    m, n = shape
+    a0 = rand_matrix(np.random.default_rng([44, m, n]), m, n, np.float64)
+    ops = rfb200.trace_lu(m, n, np.float64, pinned_host=True, early_mode=mode)
+    got, ipiv, info, snaps = replay(a0.copy(order="F"), ops)
+    want, wp, winfo = O.lu_c(a0.copy(order="F"), blocksize=64, threshold=1)
+    assert info == winfo == 0 and np.array_equal(ipiv, wp) and np.array_equal(got, want)
+    check_early_downloads(snaps, got, mode)
+    if mode == 0:
+        assert not snaps and np.array_equal(ops, rfb200.trace_lu(m, n, np.float64))
+    if mode == 2:
+        assert sum(b.size for _, _, b in snaps) == m * n
+        # what is still to be sent when the last panel finishes is the last unit's band only
+        last_panel = int(np.nonzero(ops[:, 0] == PANEL)[0][-1])
+        after = ops[last_panel + 1:]
+        after = after[after[:, 0] == DOWNLOAD]
+        assert len(after) == 1 and int(after[0, 3]) * int(after[0, 4]) <= (m - (n - 512 if n > 512 else 0)) * n
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -109,7 +146,11 @@ def test_schedule_shape_facts():
     eager = rfb200.trace_lu(16384, 16384, pinned_host=True)
     ek = eager[:, 0].tolist()
     assert ek.count(PANEL) == 256 and ek.count(GEMM) == 255
-    down = eager[eager[:, 0] == DOWNLOAD]
+    down = eager[eager[:, 0] == DOWNLOAD]                      # tiles: 32 unit bands + 31 U12 blocks, the whole matrix once
+    assert len(down) == 63 and int((down[:, 3] * down[:, 4]).sum()) == 16384 * 16384
+    assert down[-1, 1:5].tolist() == [15872, 0, 512, 16384]   # still to be sent after the last panel: 512 x n
+    bands = rfb200.trace_lu(16384, 16384, pinned_host=True, early_mode=1)
+    down = bands[bands[:, 0] == DOWNLOAD]
     assert down[:, 1].tolist() == [0, 8192, 12288, 14336, 15360] and int(down[:, 3].sum()) == 15872   # tail: last 512 rows
     # Float32 splits at multiples of 16 (src/lu.jl:158-162)
     f32 = rfb200.trace_lu(8192, 8192, np.float32)
