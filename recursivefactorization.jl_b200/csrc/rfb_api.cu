@@ -537,7 +537,11 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
     // Pipelined upload: column chunks go up on the copy stream in order; the factorization is
     // left-looking, so it starts as soon as the first chunk is resident and the rest of the upload
     // hides behind the work on the left columns.
-    // Chunks grow geometrically from 8 MB to 64 MB: the first panel only waits for the first 8 MB.
+    // The first panel only waits for the first 8 MB, and the next 15 chunks stay at 8 MB too: at the start a 64-column
+    // leaf step costs about what its columns take to upload (~150 us at 16384 rows), and a chunk is only usable when
+    // ALL of it has arrived -- doubling the chunks right away made each of the first steps wait for a chunk twice as
+    // long as the one before (~0.5 ms in total at 16384^2).  After that the factorization is far ahead of its need
+    // and the chunks grow geometrically to 64 MB.
     std::vector<int64_t> bounds;
     {
         const size_t col_bytes = sizeof(T) * (size_t)ldd;
@@ -547,7 +551,7 @@ int lu_entry(rfb_ctx *ctx, T *A, int64_t m, int64_t n, int64_t lda, int64_t *ipi
             const int64_t nc = std::max<int64_t>(64, (int64_t)(target / col_bytes));
             j = std::min<int64_t>(n, j + nc);
             bounds.push_back(j);
-            if (target < (size_t(64) << 20)) target *= 2;
+            if (bounds.size() >= 16 && target < (size_t(64) << 20)) target *= 2;
         }
     }
     const int nchunks = (int)bounds.size();

@@ -70,6 +70,14 @@ function destroy!(ctx::Context)
     return
 end
 
+# How lu! on a PAGE-LOCKED matrix sends finished factors back while it is still factoring (rfb_set_early_download):
+# 2 = finished tiles (default), 1 = row bands at the right spine of the recursion, 0 = off.  Results are identical.
+function set_early_download!(ctx::Context, mode::Integer)
+    rc = ccall((:rfb_set_early_download, librfb200), Cint, (Ptr{Cvoid}, Cint), ctx.handle, mode)
+    rc == 0 || error("librfb200 error $rc: $(last_error(ctx))")
+    return ctx
+end
+
 # one context per task (a context is not thread-safe, see rfb200.h)
 default_context() = get!(() -> Context(parse(Int, get(ENV, "LOCAL_RANK", "0"))), task_local_storage(), :rfb200_ctx)::Context
 
