@@ -469,14 +469,10 @@ def run_ours(args, rank, world, local_rank):
         hwork = ctx.pinned_empty((n, n), np.float64)
         ipiv_h = np.empty(n, dtype=np.int64)
 
-        def e2e_ms(reps, warm=True):
+        def e2e_ms(reps):
             et = []
             for it in range(1 + reps):
-                np.copyto(hwork, host)         # restore the in-place input: ~0.4 s of host memcpy with an idle GPU ...
-                if warm:
-                    work.copy_from(pristine)   # ... so one untimed device-resident factorization brings the clocks back
-                    work.lu()                  # up (a cold first kernel has read 20 % low, see the DMMA peak above);
-                    ctx.sync()                 # nothing of it is left in flight when the timed call starts
+                np.copyto(hwork, host)         # restore the in-place input (untimed)
                 barrier()
                 t = time.perf_counter()
                 rfb200.lu_(hwork, ipiv_h, ctx=ctx)
@@ -489,7 +485,6 @@ def run_ours(args, rank, world, local_rank):
         ctx.set_early_download(1)
         bands_ms = e2e_ms(2)
         ctx.set_early_download(2)
-        cold_ms = e2e_ms(2, warm=False)        # what rounds 1 and 2 reported so far: every call starts on an idle GPU
         e_ms = e2e_ms(min(args.steps, 3))
         # what was just timed must be a correct factorization too (this path uploads in column chunks, applies
         # the interchanges eagerly and downloads finished rows early: a different schedule from the device path)
@@ -502,10 +497,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": world * lu_flops(n) / (e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + n * 8 + 8,
                "pcie_h2d_GBps": n * n * 8 / h2d_s / 1e9, "pcie_d2h_GBps": n * n * 8 / d2h_s / 1e9,
-               "early_download": "tiles (rfb_set_early_download 2, the default)", "ms_per_step_row_bands": bands_ms,
-               "ms_per_step_cold": cold_ms,
-               "warm": "an untimed device-resident factorization runs to completion right before every timed call "
-                       "(the host-side restore of the 2 GB input leaves the GPU idle for ~0.4 s)"}
+               "early_download": "tiles (rfb_set_early_download 2, the default)", "ms_per_step_row_bands": bands_ms}
 
     # ---- the other single-GPU BASELINE configs and the widened rows, device resident (not the headline) ----
     others = None
