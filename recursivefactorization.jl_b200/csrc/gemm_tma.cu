@@ -74,6 +74,11 @@ __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, doubl
 __device__ __forceinline__ int a_row_in_box(int g, int t) { return (g & 1) + ((g >> 1) & 1) * 8 + (g >> 2) * 2 + t * 4; }
 __device__ __forceinline__ int b_col_in_tile(int f) { return (f & 3) * 2 + (f >> 2); }
 
+// REDUCE_EPI: full 128 x 128 tiles leave through the TMA engine as bulk f64 reduce-adds into C (SASS
+// UBLKRED.G.S.ADD.F64.RN, one 1 KB column segment per operation): the SM parks -acc in shared memory and never
+// reads C -- the addition C + (-acc) is done once, round-to-nearest, at L2 (bit-identical to C - acc).  Ragged
+// edge tiles keep the read-modify-write below (a bulk operation needs 16-byte sizes and cannot be predicated per row).
+template <bool REDUCE_EPI>
 __global__ void __launch_bounds__(TTHREADS, 1)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     double *__restrict__ C, int M, int N, int K, long long lda, int tiles_m, int tiles_n) {
@@ -196,6 +201,30 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // loads in flight per thread (a direct per-fragment RMW serialises 64 load->store round trips).
     __syncthreads();                                   // every warp is done reading the last stage
     double *sC = reinterpret_cast<double *>(base);     // [n 0..127][m 0..127]
+    if (REDUCE_EPI && m0 + TBM <= M && n0 + TBN <= N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = wm + (i >> 1) * kABoxRows + a_row_in_box(g, i & 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = wn + j * 8 + b_col_in_tile(2 * q + e);
+                    sC[c * TBM + r] = -acc[i][j][e];
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
+        __syncthreads();
+        if (tid < TBN) {                               // one 1 KB column segment per thread
+            double *gp = C + m0 + (long long)(n0 + tid) * lda;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                         ::"l"(gp), "r"(smem_u32(sC + tid * TBM)), "r"(TBM * 8) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // performed before the CTA (and the kernel) ends
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = wm + (i >> 1) * kABoxRows + a_row_in_box(g, i & 1);
@@ -272,10 +301,19 @@ int rfb_launch_gemm_f64_tma(rfb_ctx *ctx, double *C, const double *A, const doub
     CUtensorMap mapA, mapB;
     if (!make_map(ctx, &mapA, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda * 8, kABoxRows, TBK)) return RFB_OK;
     if (!make_map(ctx, &mapB, B, (uint64_t)k, (uint64_t)n, (uint64_t)lda * 8, TBK, TBN)) return RFB_OK;
-    RFB_TRY(rfb_ensure_smem(ctx, (const void *)gemm_f64_tma_kernel, kTmaSmem));
     const int tiles_m = (int)((m + TBM - 1) / TBM), tiles_n = (int)((n + TBN - 1) / TBN);
+    if (ctx->gemm_reduce_epilogue) {
+        RFB_TRY(rfb_ensure_smem(ctx, (const void *)gemm_f64_tma_kernel<true>, kTmaSmem));
+        RfbLaunchScope scope(ctx, RFB_KC_GEMM, 2.0 * (double)m * (double)n * (double)k);
+        gemm_f64_tma_kernel<true><<<(unsigned int)(tiles_m * tiles_n), TTHREADS, kTmaSmem, ctx->stream>>>(
+            mapA, mapB, C, (int)m, (int)n, (int)k, lda, tiles_m, tiles_n);
+        RFB_CUDA(ctx, cudaGetLastError());
+        *handled = true;
+        return RFB_OK;
+    }
+    RFB_TRY(rfb_ensure_smem(ctx, (const void *)gemm_f64_tma_kernel<false>, kTmaSmem));
     RfbLaunchScope scope(ctx, RFB_KC_GEMM, 2.0 * (double)m * (double)n * (double)k);
-    gemm_f64_tma_kernel<<<(unsigned int)(tiles_m * tiles_n), TTHREADS, kTmaSmem, ctx->stream>>>(
+    gemm_f64_tma_kernel<false><<<(unsigned int)(tiles_m * tiles_n), TTHREADS, kTmaSmem, ctx->stream>>>(
         mapA, mapB, C, (int)m, (int)n, (int)k, lda, tiles_m, tiles_n);
     RFB_CUDA(ctx, cudaGetLastError());
     *handled = true;

@@ -696,6 +696,7 @@ int rfb_create(rfb_ctx **out, int device) {
     RFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
     RFB_CUDA(ctx, cudaMalloc(&ctx->xchg, sizeof(RfbPanelXchg)));
     RFB_CUDA(ctx, cudaMemset(ctx->xchg, 0, sizeof(RfbPanelXchg)));
+    if (const char *e = getenv("RFB_GEMM_EPILOGUE")) ctx->gemm_reduce_epilogue = atoi(e) != 0;
     if (const char *e = getenv("RFB_LASWP_NET_MIN")) ctx->laswp_net_min = atoll(e);
     if (const char *e = getenv("RFB_LASWP_NET_CAP")) ctx->laswp_net_cap = atoll(e);
     for (int l = 0; l < rfb_ctx::kLanes; ++l) {
