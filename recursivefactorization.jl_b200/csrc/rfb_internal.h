@@ -91,7 +91,7 @@ struct rfb_ctx {
     int gemm_persist = 0;                 // K4 Float64: persistent kernel, ring running across tiles (env RFB_GEMM_PERSIST=1)
     int64_t gemm_persist_max_k = int64_t(1) << 40;    // ... for inner dimensions up to this (env RFB_GEMM_PERSIST_MAXK)
     int64_t gemm_persist_min_tiles = 1;               // ... and at least this many tiles (env RFB_GEMM_PERSIST_MINTILES)
-    int gemm_reduce_epilogue = 0;         // K4 Float64: full tiles leave as TMA bulk f64 reduce-adds (env RFB_GEMM_EPILOGUE=1)
+    int gemm_reduce_epilogue = 1;         // K4 Float64: full tiles leave as TMA bulk f64 reduce-adds (default; env RFB_GEMM_EPILOGUE=0: SM-side read-modify-write)
     int64_t laswp_net_min = 512;          // pivot ranges at least this long take the node-level path (env RFB_LASWP_NET_MIN)
     int64_t laswp_net_cap = 0;            // pivots per chunk, 0 = kernel default (env RFB_LASWP_NET_CAP; tests shrink it)
 
