@@ -657,6 +657,19 @@ int solve_kept(rfb_ctx *ctx, int64_t id, T *B, int64_t nrhs, int64_t ldb) {
     return RFB_OK;
 }
 
+// A host-mode call that fails after it has enqueued asynchronous copies from / into the caller's buffers must not return
+// while a DMA can still touch them (the library never keeps a host pointer past a call): drain every stream of the context.
+static int drained(rfb_ctx *ctx, int rc) {
+    if (rc != RFB_OK && ctx && ctx->stream && !ctx->dry_run) {
+        cudaSetDevice(ctx->device);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        if (ctx->down_stream) cudaStreamSynchronize(ctx->down_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -932,19 +945,19 @@ int rfb_trsm_lunn_f32(rfb_ctx *ctx, const float *U, int64_t k, float *B, int64_t
 }
 int rfb_solve_f64(rfb_ctx *ctx, const double *LU, int64_t n, int64_t lda, const int64_t *ipiv, double *B, int64_t nrhs,
                   int64_t ldb, const rfb_opts *opts) {
-    return solve_entry<double>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts);
+    return drained(ctx, solve_entry<double>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts));
 }
 int rfb_solve_f32(rfb_ctx *ctx, const float *LU, int64_t n, int64_t lda, const int64_t *ipiv, float *B, int64_t nrhs,
                   int64_t ldb, const rfb_opts *opts) {
-    return solve_entry<float>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts);
+    return drained(ctx, solve_entry<float>(ctx, LU, n, lda, ipiv, B, nrhs, ldb, opts));
 }
 int rfb_kept_id(rfb_ctx *ctx, int64_t *id) {
     if (!ctx || !id) return RFB_ERR_ARG;
     *id = ctx->kept.valid ? ctx->kept.id : 0;
     return RFB_OK;
 }
-int rfb_solve_kept_f64(rfb_ctx *ctx, int64_t id, double *B, int64_t nrhs, int64_t ldb) { return solve_kept<double>(ctx, id, B, nrhs, ldb); }
-int rfb_solve_kept_f32(rfb_ctx *ctx, int64_t id, float *B, int64_t nrhs, int64_t ldb) { return solve_kept<float>(ctx, id, B, nrhs, ldb); }
+int rfb_solve_kept_f64(rfb_ctx *ctx, int64_t id, double *B, int64_t nrhs, int64_t ldb) { return drained(ctx, solve_kept<double>(ctx, id, B, nrhs, ldb)); }
+int rfb_solve_kept_f32(rfb_ctx *ctx, int64_t id, float *B, int64_t nrhs, int64_t ldb) { return drained(ctx, solve_kept<float>(ctx, id, B, nrhs, ldb)); }
 int rfb_panel_getrf_nopiv_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t *info_dev, int64_t col_offset) {
     RFB_CHECK_CTX(ctx);
     return rfb_launch_panel_nopiv<double>(ctx, A, m, n, lda, info_dev, col_offset);
@@ -975,19 +988,19 @@ int rfb_butterfly_vec_f32(rfb_ctx *ctx, float *B, int64_t n, int64_t nrhs, int64
 }
 int rfb_butterfly_solve_f64(rfb_ctx *ctx, const double *A, int64_t n, int64_t lda, double *B, int64_t nrhs, int64_t ldb,
                             const double *uv, int64_t *info, const rfb_opts *opts) {
-    return butterfly_solve_entry<double>(ctx, A, n, lda, B, nrhs, ldb, uv, info, opts);
+    return drained(ctx, butterfly_solve_entry<double>(ctx, A, n, lda, B, nrhs, ldb, uv, info, opts));
 }
 int rfb_butterfly_solve_f32(rfb_ctx *ctx, const float *A, int64_t n, int64_t lda, float *B, int64_t nrhs, int64_t ldb,
                             const float *uv, int64_t *info, const rfb_opts *opts) {
-    return butterfly_solve_entry<float>(ctx, A, n, lda, B, nrhs, ldb, uv, info, opts);
+    return drained(ctx, butterfly_solve_entry<float>(ctx, A, n, lda, B, nrhs, ldb, uv, info, opts));
 }
 int rfb_lu_batched_f64(rfb_ctx *ctx, double *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
                        int64_t *ipiv, int64_t *info, const rfb_opts *opts) {
-    return lu_batched_entry<double>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts);
+    return drained(ctx, lu_batched_entry<double>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts));
 }
 int rfb_lu_batched_f32(rfb_ctx *ctx, float *A, int64_t m, int64_t n, int64_t lda, int64_t stride_a, int64_t batch,
                        int64_t *ipiv, int64_t *info, const rfb_opts *opts) {
-    return lu_batched_entry<float>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts);
+    return drained(ctx, lu_batched_entry<float>(ctx, A, m, n, lda, stride_a, batch, ipiv, info, opts));
 }
 int rfb_ipiv_shift(rfb_ctx *ctx, int64_t *ipiv_dev, int64_t n, int64_t shift) {
     RFB_CHECK_CTX(ctx);
