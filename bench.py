@@ -422,8 +422,15 @@ def run_ours(args, rank, world, local_rank):
               "max_abs_L": lmax}
     if args.check_pivots:                       # north_star: "pivot indices bit-exact" -- at the headline size, every run
         from scipy.linalg import lapack
-        _, piv, _ = lapack.dgetrf(np.array(host, order="F", copy=True), overwrite_a=True)
+        a_l = np.array(host, order="F", copy=True)
+        t_l = time.perf_counter()
+        _, piv, _ = lapack.dgetrf(a_l, overwrite_a=True)
+        t_l = time.perf_counter() - t_l
+        del a_l
         checks["pivots_equal_lapack"] = bool(np.array_equal(ipiv, piv + 1))
+        # the stronger CPU sanity baseline, timed on the same matrix on this box's host cores
+        checks["lapack_dgetrf_gflops"] = lu_flops(n) / t_l / 1e9
+        checks["lapack_dgetrf_cores"] = os.cpu_count() or 1
         if not checks["pivots_equal_lapack"]:
             checks["first_pivot_mismatch"] = int(np.argmax(ipiv != piv + 1))
         del piv
@@ -511,6 +518,7 @@ def run_ours(args, rank, world, local_rank):
         n_s = min(n, args.cpu_sample_n)
         gf, secs = cpu_baseline(n_s, cores)
         cpu = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "seconds": secs,
+               "lapack_dgetrf_gflops_same_matrix": checks.get("lapack_dgetrf_gflops"),
                "sample": f"{n_s}x{n_s} Float64 U[0,1) LU, oracle/rf_oracle.c (C restatement of src/lu.jl, reference "
                          f"defaults), OpenMP {cores} threads; the Julia reference cannot run here"}
 
