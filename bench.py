@@ -9,14 +9,21 @@ U[0,1) matrix (numpy default_rng(12), the distribution of test/runtests.jl:45).
 ours:       value = device-resident throughput (matrix already in HBM, CUDA events on the library's
             stream around each factorization; the restore copy between steps is outside the timed
             region); e2e = the same metric through the public host API (`rfb200.lu_` on a pinned host
-            matrix: H2D + LU + D2H inside the timed region).
+            matrix: H2D + LU + D2H inside the timed region; finished tiles of the factors travel back
+            while the factorization runs, the older row-band scheme is timed beside it);
+            roofline = all K4 launches of one LU against max(DMMA microbenchmark, pipe rate at the
+            maximum SM clock); checks = residual, pivots against LAPACK dgetrf (also timed).
 reference:  the reference is pure Julia and cannot run here (no Julia runtime), so
             this arm times the CPU oracle port of its algorithm (oracle/rf_oracle.c, all host cores)
-            on a bounded sample of the same workload.
+            at the SAME size as the product arm whenever steps + warmup factorizations fit its time
+            budget (--ref-budget-s), otherwise on the largest sample that does (`same_config` says
+            which); with a Julia runtime under baseline/_ref it runs the real package instead.
 
 N > 1 (torchrun, one process per GPU): ONE 32768 x 32768 matrix (BASELINE config 4) is factored by all
-ranks together -- 1-D block-cyclic columns, owner-rooted NCCL broadcast of each factored block column
-(recursivefactorization.jl_b200/dist_lu.py); strong scaling, value = 2n^3/3 / max-over-ranks time.
+ranks together -- 1-D block-cyclic block columns, owner-rooted NCCL broadcast of each factored block
+column, C++ scheduler behind rfb_mg_* (csrc/rfb_mg.cu; dist_lu.py is a thin ctypes caller); strong
+scaling, value = 2n^3/3 / max-over-ranks time; the same matrix is also factored on ONE GPU in the same
+run (`strong_n1_value`, pivot equality).
 """
 import argparse
 import json
