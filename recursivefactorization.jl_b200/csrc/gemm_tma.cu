@@ -271,201 +271,6 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-// ----------------------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks its tiles (tile = blockIdx.x + i * gridDim.x, the same grouped
-// rasterisation), and the k-tile ring does NOT drain at a tile boundary: the producer keeps running PSTAGES - 1 k-tiles
-// ahead ACROSS tiles, so the first operands of tile i + 1 land while tile i is still multiplying, and a finished tile
-// leaves through the TMA engine (bulk f64 reduce-add into C, see REDUCE_EPI above) from a staging tile of its own
-// while the next one is already running.  Per tile the SM loses one park of the accumulators (64 st.shared per
-// thread + two barriers) instead of a pipeline fill, an HBM round trip for C and a CTA launch: the one-tile-per-CTA
-// kernel pays ~11 us per wave for those (8192 x 8192 x 64: 16.5 us per wave for 8.4 us of DMMAs), which is what kept
-// the k <= 1024 launches of an LU at 0.45 - 0.9 of the DMMA peak.  Shared memory: 3 stages x 32 KB + the 128 KB
-// staging tile (4 stages would not fit beside it).
-// ----------------------------------------------------------------------------------------------------------------
-constexpr int PSTAGES = 3;
-constexpr size_t kPersistSmem = (size_t)PSTAGES * kStageBytes + (size_t)TBM * TBN * 8 + 1024 /*align slack*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ void tile_origin(int pid, int tiles_m, int tiles_n, int &m0, int &n0) {
-    const int in_group = kGroupM * tiles_n;
-    const int group = pid / in_group;
-    const int first_m = group * kGroupM;
-    const int gsz = min(tiles_m - first_m, kGroupM);
-    m0 = (first_m + (pid % in_group) % gsz) * TBM;
-    n0 = ((pid % in_group) / gsz) * TBN;
-}
-
-__global__ void __launch_bounds__(TTHREADS, 1)
-gemm_f64_tma_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                            double *__restrict__ C, int M, int N, int K, long long lda, int tiles_m, int tiles_n) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    double *sC = reinterpret_cast<double *>(base + (size_t)PSTAGES * kStageBytes);          // [n 0..127][m 0..127]
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(base + (size_t)PSTAGES * kStageBytes + (size_t)TBM * TBN * 8);
-    unsigned long long *empty = full + PSTAGES;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total_tiles = tiles_m * tiles_n;
-    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // blockIdx.x < total_tiles
-    const int KT = (K + TBK - 1) / TBK;
-    const int total_g = my_tiles * KT;                     // k-tiles this CTA consumes, over all of its tiles
-
-    if (tid == 0) {
-        for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TCONSUMER_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    const bool producer = (warp == 0 && lane == 0);
-    auto produce = [&](int pg) {          // fill the ring slot of this CTA's pg-th k-tile (one elected lane)
-        const int ptile = pg / KT, pkt = pg - ptile * KT;
-        int pm0, pn0;
-        tile_origin((int)blockIdx.x + ptile * (int)gridDim.x, tiles_m, tiles_n, pm0, pn0);
-        const int s2 = pg % PSTAGES;
-        const int use = pg / PSTAGES;
-        if (use > 0) mbar_wait(&empty[s2], (unsigned int)(use - 1) & 1u);   // consumers drained the previous use
-        mbar_expect_tx(&full[s2], kStageBytes);
-        unsigned char *dA = base + (size_t)s2 * kStageBytes;
-        unsigned char *dB = dA + kStageABytes;
-#pragma unroll
-        for (int b = 0; b < kABoxes; ++b)
-            tma_load_2d(dA + b * (kABoxRows * TBK * 8), &mapA, pm0 + b * kABoxRows, pkt * TBK, &full[s2]);
-        tma_load_2d(dB, &mapB, pkt * TBK, pn0, &full[s2]);
-    };
-    if (producer) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        for (int pg = 0; pg < PSTAGES - 1 && pg < total_g; ++pg) produce(pg);
-    }
-    __syncwarp();
-
-    // DMMA consumers: 8 warps as 2 (m) x 4 (n), warp tile 64 x 32 (fragment maps as in the kernel above)
-    const int g = lane >> 2, q = lane & 3;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
-    int a_off[2][2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const int r = a_row_in_box(g, t);
-#pragma unroll
-        for (int kp = 0; kp < 2; ++kp) {
-            const int k7 = kp * 4 + q;
-            a_off[t][kp] = q * 16 + ((((r >> 1) ^ k7) & 7) << 1) + (r & 1);
-        }
-    }
-    const int bn = b_col_in_tile(g);
-    int b_off[4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) b_off[ks] = (wn + bn) * 16 + ((((ks * 2 + (q >> 1)) ^ bn) & 7) << 1) + (q & 1);
-
-    int cg = 0;                 // k-tiles consumed so far (all tiles)
-    int s = 0;                  // ring slot of k-tile cg
-    unsigned int ph = 0;        // its phase parity
-    for (int t = 0; t < my_tiles; ++t) {
-        int m0, n0;
-        tile_origin((int)blockIdx.x + t * (int)gridDim.x, tiles_m, tiles_n, m0, n0);
-        // pull this tile of C into L2: the reduce-add (or the ragged tile's read-modify-write) then works on L2 lines
-        {
-            const int rr = (tid & 7) * 16;
-#pragma unroll
-            for (int c = tid >> 3; c < TBN; c += TTHREADS / 8) {
-                if (m0 + rr < M && n0 + c < N) {
-                    const double *p = C + (m0 + rr) + (long long)(n0 + c) * lda;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                }
-            }
-        }
-        double acc[8][4][2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        for (int kt = 0; kt < KT; ++kt) {
-            if (producer && cg + PSTAGES - 1 < total_g) produce(cg + PSTAGES - 1);
-            __syncwarp();
-            mbar_wait(&full[s], ph);
-            const double *tA = reinterpret_cast<const double *>(base + (size_t)s * kStageBytes) + (wm / kABoxRows) * (kABoxRows * TBK);
-            const double *tB = reinterpret_cast<const double *>(base + (size_t)s * kStageBytes + kStageABytes);
-#pragma unroll
-            for (int ks = 0; ks < TBK / 4; ++ks) {
-                double a[8], b[4];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    a[i] = tA[(i >> 1) * (kABoxRows * TBK) + ks * 64 + a_off[i & 1][ks & 1]];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = tB[j * 128 + b_off[ks]];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            ++cg;
-            if (++s == PSTAGES) { s = 0; ph ^= 1u; }
-        }
-
-        // ---- epilogue of tile t (the ring already holds the first k-tiles of tile t + 1) ----
-        if (tid < TBN) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile t - 1 has left the staging tile
-        __syncthreads();
-        const bool full_tile = (m0 + TBM <= M) && (n0 + TBN <= N);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = wm + (i >> 1) * kABoxRows + a_row_in_box(g, i & 1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = wn + j * 8 + b_col_in_tile(2 * q + e);
-                    sC[c * TBM + r] = -acc[i][j][e];
-                }
-            }
-        }
-        if (full_tile) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
-            __syncthreads();
-            if (tid < TBN) {                           // C[:, n0 + tid] += staging column (one 1 KB bulk reduce per thread)
-                double *gp = C + m0 + (long long)(n0 + tid) * lda;
-                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
-                             ::"l"(gp), "r"(smem_u32(sC + tid * TBM)), "r"(TBM * 8) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        } else {
-            // ragged edge tile: coalesced 16-byte read-modify-write, predicated per element (C + (-acc))
-            __syncthreads();
-            const int rp = (tid & 63) * 2;
-            const int cb = tid >> 6;
-            const int gr = m0 + rp;
-#pragma unroll
-            for (int it0 = 0; it0 < TBN / 4; it0 += 8) {
-                double2 cv[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int gc = n0 + cb + 4 * (it0 + u);
-                    cv[u] = make_double2(0.0, 0.0);
-                    if (gc < N) {
-                        const double *p = C + gr + (long long)gc * lda;
-                        if (gr + 1 < M) cv[u] = *reinterpret_cast<const double2 *>(p);
-                        else if (gr < M) cv[u].x = *p;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int c = cb + 4 * (it0 + u);
-                    const int gc = n0 + c;
-                    if (gc < N) {
-                        const double2 a2 = *reinterpret_cast<const double2 *>(sC + c * TBM + rp);
-                        double *p = C + gr + (long long)gc * lda;
-                        if (gr + 1 < M) *reinterpret_cast<double2 *>(p) = make_double2(cv[u].x + a2.x, cv[u].y + a2.y);
-                        else if (gr < M) *p = cv[u].x + a2.x;
-                    }
-                }
-            }
-        }
-    }
-    if (tid < TBN) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every reduce-add performed before the CTA ends
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -497,17 +302,6 @@ int rfb_launch_gemm_f64_tma(rfb_ctx *ctx, double *C, const double *A, const doub
     if (!make_map(ctx, &mapA, A, (uint64_t)m, (uint64_t)k, (uint64_t)lda * 8, kABoxRows, TBK)) return RFB_OK;
     if (!make_map(ctx, &mapB, B, (uint64_t)k, (uint64_t)n, (uint64_t)lda * 8, TBK, TBN)) return RFB_OK;
     const int tiles_m = (int)((m + TBM - 1) / TBM), tiles_n = (int)((n + TBN - 1) / TBN);
-    if (ctx->gemm_persist && k <= ctx->gemm_persist_max_k && (int64_t)tiles_m * tiles_n >= ctx->gemm_persist_min_tiles) {
-        RFB_TRY(rfb_ensure_smem(ctx, (const void *)gemm_f64_tma_persist_kernel, kPersistSmem));
-        const int64_t total = (int64_t)tiles_m * tiles_n;
-        const unsigned int grid = (unsigned int)(total < ctx->sm_count ? total : ctx->sm_count);
-        RfbLaunchScope scope(ctx, RFB_KC_GEMM, 2.0 * (double)m * (double)n * (double)k);
-        gemm_f64_tma_persist_kernel<<<grid, TTHREADS, kPersistSmem, ctx->stream>>>(mapA, mapB, C, (int)m, (int)n, (int)k, lda,
-                                                                                   tiles_m, tiles_n);
-        RFB_CUDA(ctx, cudaGetLastError());
-        *handled = true;
-        return RFB_OK;
-    }
     if (ctx->gemm_reduce_epilogue) {
         RFB_TRY(rfb_ensure_smem(ctx, (const void *)gemm_f64_tma_kernel<true>, kTmaSmem));
         RfbLaunchScope scope(ctx, RFB_KC_GEMM, 2.0 * (double)m * (double)n * (double)k);

@@ -710,9 +710,6 @@ int rfb_create(rfb_ctx **out, int device) {
     RFB_CUDA(ctx, cudaMalloc(&ctx->xchg, sizeof(RfbPanelXchg)));
     RFB_CUDA(ctx, cudaMemset(ctx->xchg, 0, sizeof(RfbPanelXchg)));
     if (const char *e = getenv("RFB_GEMM_EPILOGUE")) ctx->gemm_reduce_epilogue = atoi(e) != 0;
-    if (const char *e = getenv("RFB_GEMM_PERSIST")) ctx->gemm_persist = atoi(e) != 0;
-    if (const char *e = getenv("RFB_GEMM_PERSIST_MAXK")) ctx->gemm_persist_max_k = atoll(e);
-    if (const char *e = getenv("RFB_GEMM_PERSIST_MINTILES")) ctx->gemm_persist_min_tiles = atoll(e);
     if (const char *e = getenv("RFB_LASWP_NET_MIN")) ctx->laswp_net_min = atoll(e);
     if (const char *e = getenv("RFB_LASWP_NET_CAP")) ctx->laswp_net_cap = atoll(e);
     for (int l = 0; l < rfb_ctx::kLanes; ++l) {

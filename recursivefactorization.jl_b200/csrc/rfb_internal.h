@@ -88,9 +88,6 @@ struct rfb_ctx {
     int *net_meta() const { return net_meta_[lane]; }
     int *net_srcmap() const { return net_srcmap_[lane]; }
     int *net_clist() const { return net_clist_[lane]; }
-    int gemm_persist = 0;                 // K4 Float64: persistent kernel, ring running across tiles (env RFB_GEMM_PERSIST=1)
-    int64_t gemm_persist_max_k = int64_t(1) << 40;    // ... for inner dimensions up to this (env RFB_GEMM_PERSIST_MAXK)
-    int64_t gemm_persist_min_tiles = 1;               // ... and at least this many tiles (env RFB_GEMM_PERSIST_MINTILES)
     int gemm_reduce_epilogue = 1;         // K4 Float64: full tiles leave as TMA bulk f64 reduce-adds (default; env RFB_GEMM_EPILOGUE=0: SM-side read-modify-write)
     int64_t laswp_net_min = 512;          // pivot ranges at least this long take the node-level path (env RFB_LASWP_NET_MIN)
     int64_t laswp_net_cap = 0;            // pivots per chunk, 0 = kernel default (env RFB_LASWP_NET_CAP; tests shrink it)

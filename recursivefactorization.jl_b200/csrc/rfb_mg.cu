@@ -559,9 +559,6 @@ int rank_create(MgRank *r) {
     int rc = rfb_create(&ctx, r->device);
     r->ctx = ctx;
     if (rc != RFB_OK) return r->fail(rc, "%s", ctx ? ctx->last_error.c_str() : "rfb_create failed");
-    // The persistent K4 kernel pins one CTA on every SM for a whole launch; beside the broadcast kernels of the
-    // communication stream its displaced CTAs would start late and stretch every slice.  Unmeasured across GPUs: opt-in.
-    if (!getenv("RFB_MG_GEMM_PERSIST")) ctx->gemm_persist = 0;
     r->s_comp = ctx->own_stream;
     int lo = 0, hi = 0;
     MG_CUDA(r, cudaDeviceGetStreamPriorityRange(&lo, &hi));

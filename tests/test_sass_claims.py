@@ -54,8 +54,6 @@ def test_f64_trailing_gemm_is_tma_fed_dmma_with_bulk_reduce_epilogue(sass):
         assert count(ops, "UBLKRED.G.S.ADD.F64.RN") == 1, name          # the shipped epilogue (include/...)
     for name, ops in kernels(sass, "gemm_f64_tma_kernel<false>").items():
         assert count(ops, "UTMALDG.2D") >= 17 and count(ops, "DMMA.8x8x4") == 128 and count(ops, "UBLKRED") == 0, name
-    for name, ops in kernels(sass, "gemm_f64_tma_persist_kernel").items():
-        assert count(ops, "UTMALDG.2D") >= 17 and count(ops, "DMMA.8x8x4") == 128 and count(ops, "UBLKRED") == 1, name
 
 
 def test_f32_trailing_gemm_is_tcgen05_with_tmem(sass):
@@ -73,6 +71,6 @@ def test_triangular_solve_and_panel(sass):
 
 
 def test_no_local_memory_spills_in_the_gemm_kernels(sass):
-    for needle in ("gemm_f64_tma_kernel", "gemm_f64_tma_persist_kernel", "gemm_f32_tc_kernel"):
+    for needle in ("gemm_f64_tma_kernel", "gemm_f32_tc_kernel"):
         for name, ops in kernels(sass, needle).items():
             assert count(ops, "LDL") == 0 and count(ops, "STL") == 0, name
